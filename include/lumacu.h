@@ -1,0 +1,184 @@
+/*
+ * lumacu.h -- C ABI of the B200 (sm_100a) implementation of Luma HDRv's
+ * per-pixel HDR<->integer transform.
+ *
+ * This is the drop-in boundary for ONE stage of the reference codec: the path
+ *
+ *   LumaEncoder::encode  = LumaQuantizer::transformColorSpace(frame,true,sc)
+ *                          + LumaEncoder::setVpxChannel x3  (-> LumaQuantizer::quantize)
+ *   LumaDecoder::decode  = LumaDecoder::getVpxChannels (-> LumaQuantizer::dequantize)
+ *                          + LumaQuantizer::transformColorSpace(frame,false,sc)
+ *
+ * (reference: include/luma/luma_encoder.h:142-148, src/luma_encoder.cpp:260-317,
+ * include/luma/luma_decoder.h:143-161, src/luma_decoder.cpp:205-240,
+ * src/luma_quantizer.cpp:172-510).  VP9 (libvpx) and Matroska stay on the host.
+ *
+ * Conventions
+ *  - plain C types only; no exceptions cross this boundary; every call returns
+ *    a lumacu_status (0 = OK) and records a message retrievable with
+ *    lumacu_last_error().
+ *  - float frames are planar f32 exactly like LumaFrame
+ *    (include/luma/luma_frame.h:83-86): buffer[c*h*w + y*w + x], c = 0..2.
+ *  - integer planes are the vpx_image_t planes the reference fills/reads:
+ *    8-bit samples (profiles 0,1) or little-endian 16-bit samples (profiles
+ *    2,3) with a byte pitch stride[plane]; profiles 0,2 are 4:2:0 (chroma
+ *    planes ((w+1)>>1) x ((h+1)>>1)), profiles 1,3 are 4:4:4
+ *    (src/luma_encoder.cpp:121-128,265-269).
+ *  - "_dev" entry points take device pointers and a cudaStream_t (passed as
+ *    void*) and are asynchronous; the others take host pointers, stage through
+ *    pinned buffers and return when the result is in host memory.
+ *  - results are bit-identical to the reference CPU path for the integer
+ *    planes and for the decoded floats (see DESIGN.md for the one documented
+ *    libm dependency: CS_YCBCR calls powf per pixel).
+ */
+#ifndef LUMACU_H
+#define LUMACU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUMACU_VERSION 100 /* 0.1.0 */
+
+typedef enum lumacu_status {
+    LUMACU_OK = 0,
+    LUMACU_ERR_INVALID_ARGUMENT = 1,
+    LUMACU_ERR_CUDA = 2,
+    LUMACU_ERR_NOT_CONFIGURED = 3, /* lumacu_set_quantizer not called yet */
+    LUMACU_ERR_UNSUPPORTED = 4,
+    LUMACU_ERR_OUT_OF_MEMORY = 5,
+    LUMACU_ERR_NO_DEVICE = 6
+} lumacu_status;
+
+/* Wire-format enum values of the reference (include/luma/luma_quantizer.h:95-96);
+ * they are memcpy'd into Matroska attachments 432/433, so the order is fixed. */
+typedef enum lumacu_ptf {
+    LUMACU_PTF_PSI = 0,
+    LUMACU_PTF_PQ = 1,
+    LUMACU_PTF_LOG = 2,
+    LUMACU_PTF_JND_HDRVDP = 3,
+    LUMACU_PTF_LINEAR = 4
+} lumacu_ptf;
+
+typedef enum lumacu_color_space {
+    LUMACU_CS_LUV = 0,
+    LUMACU_CS_RGB = 1,
+    LUMACU_CS_YCBCR = 2,
+    LUMACU_CS_XYZ = 3
+} lumacu_color_space;
+
+/* Per-frame reduction over plane 0 after the colour transform.  sum/count is
+ * the mean the reference compares against 1.0 for its "is input calibrated?"
+ * warning (src/luma_encoder.cpp:276,294,314-316); max is an extra output the
+ * reference does not have. */
+typedef struct lumacu_frame_stats {
+    double sum;  /* sum of plane-0 samples (Y for Lu'v'), accumulated in fp64 */
+    float max;   /* max of plane-0 samples (NaNs ignored) */
+    float min;   /* min of plane-0 samples (NaNs ignored) */
+} lumacu_frame_stats;
+
+typedef struct lumacu_ctx lumacu_ctx;
+
+/* ---- library / context ------------------------------------------------------ */
+int lumacu_version(void);
+const char *lumacu_status_name(int status);
+int lumacu_device_count(int *count);
+
+/* Creates a context bound to CUDA device `device` (own stream, pinned staging
+ * buffers grown on demand).  Replaces nothing in the reference; it is the state
+ * a LumaEncoder / LumaDecoder object carries next to its LumaQuantizer. */
+int lumacu_create(int device, lumacu_ctx **out);
+int lumacu_destroy(lumacu_ctx *ctx);
+/* Message of the last failing call on `ctx` (or of the last failing
+ * lumacu_create on this thread when ctx is NULL).  Never NULL. */
+const char *lumacu_last_error(const lumacu_ctx *ctx);
+int lumacu_device(const lumacu_ctx *ctx);
+/* Block until all work queued on the context's own stream has finished. */
+int lumacu_synchronize(lumacu_ctx *ctx);
+
+/* ---- quantizer -------------------------------------------------------------- */
+/* Host-side LUT construction = the table half of LumaQuantizer::setQuantizer
+ * (src/luma_quantizer.cpp:172-212, setMapping* :114-169, transformPQ/Log
+ * :485-510).  Writes (2^bitdepth) floats to `lut_out` (capacity `cap`, in
+ * floats).  Runs on the host so that PQ/LOG entries come from the same libm
+ * (powf/log10f) the reference uses. */
+int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out,
+                     size_t cap);
+
+/* Device-side quantizer state = the fields LumaQuantizer keeps
+ * (include/luma/luma_quantizer.h:120-126): the code->luminance LUT
+ * (lut_len = maxVal+1 entries), maxValColor = 2^colorBits-1, the colour space
+ * and Lmax (used per pixel only by CS_YCBCR's PQ).  May be called again at any
+ * time, e.g. after the decoder overwrote the LUT from attachment 434
+ * (src/luma_decoder.cpp:121-122).  The encode side additionally derives exact
+ * decision thresholds from the LUT (see DESIGN.md "luma search"). */
+int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t lut_len,
+                         uint32_t max_val_color, int color_space, float max_lum);
+
+/* ---- whole-frame transform, host memory ------------------------------------- */
+/* LumaEncoder::encode minus run() (include/luma/luma_encoder.h:142-148):
+ * rgb (3*w*h f32, NOT modified unless write_back != 0, in which case it
+ * receives the colour-transformed planes exactly like the reference's in-place
+ * side effect, src/luma_quantizer.cpp:281-313) -> planes[0..2].
+ * w and h must be even and > 0 (src/luma_encoder.cpp:118-119).
+ * stats may be NULL. */
+int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile,
+                  float pre_scaling, uint8_t *const planes[3], const int32_t strides[3],
+                  int write_back, lumacu_frame_stats *stats);
+
+/* LumaDecoder::decode minus run() (include/luma/luma_decoder.h:143-161):
+ * planes -> rgb (3*w*h f32). */
+int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
+                  uint32_t w, uint32_t h, int profile, float pre_scaling, float *rgb);
+
+/* LumaQuantizer::transformColorSpace(frame, toCs, sc) (src/luma_quantizer.cpp:
+ * 267-482): in-place colour transform of a planar f32 frame. */
+int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs,
+                                 float sc);
+
+/* Element-wise LumaQuantizer::quantize / dequantize (src/luma_quantizer.cpp:
+ * 215-264) over n values of channel `ch`; codes are returned as floats like
+ * the reference does. */
+int lumacu_quantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch);
+int lumacu_dequantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch);
+
+/* ---- whole-frame transform, device memory (asynchronous) -------------------- */
+/* Batched: n_frames frames per launch.  Frame f reads d_rgb + f*rgb_frame_stride
+ * (in floats; 0 means 3*w*h) and writes d_planes[p] + f*plane_frame_stride[p]
+ * (bytes).  d_stats (device pointer, n_frames entries) may be NULL.
+ * d_rgb_out, if not NULL, receives the colour-transformed frame (the
+ * reference's in-place side effect); it may alias d_rgb. */
+int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, uint32_t w,
+                      uint32_t h, int profile, float pre_scaling, uint8_t *const d_planes[3],
+                      const int32_t strides[3], uint32_t n_frames, size_t rgb_frame_stride,
+                      const size_t plane_frame_stride[3], lumacu_frame_stats *d_stats,
+                      void *stream);
+
+int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3],
+                      uint32_t w, uint32_t h, int profile, float pre_scaling, float *d_rgb,
+                      uint32_t n_frames, size_t rgb_frame_stride,
+                      const size_t plane_frame_stride[3], void *stream);
+
+int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame, uint32_t w, uint32_t h,
+                                     int to_cs, float sc, void *stream);
+int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch,
+                        void *stream);
+int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch,
+                          void *stream);
+
+/* ---- introspection (used by bench.py / tests) -------------------------------- */
+/* Number of kernels this context has launched so far. */
+uint64_t lumacu_launch_count(const lumacu_ctx *ctx);
+/* Describes how the luma search was configured by the last set_quantizer:
+ * mode 0 = bucket table + threshold walk in shared memory, 1 = exact binary
+ * search replica in global memory. */
+int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift,
+                       uint32_t *walk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMACU_H */
