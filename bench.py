@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the HDR<->integer transform round trip (encode + decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json metric): 3840x2160 float32 RGB frames, PQ transfer function, Lu'v'
+11-bit luma / 8-bit chroma, profile 2 (4:2:0, LE-u16 planes).  One step = one pass of the hot
+path over one batch of `--frames` distinct synthetic frames per GPU: LumaEncoder::encode (minus
+VP9) for every frame, then LumaDecoder::decode for every frame.
+
+* value      device-resident throughput (inputs/outputs in HBM), CUDA events, max over ranks
+* e2e        same metric through the host-pointer C ABI (lumacu_encode / lumacu_decode) with pinned
+             host buffers; H2D/D2H copies inside the timed region
+* roofline   algorithmic bytes (15 B/px per direction) / measured kernel time vs the measured HBM peak
+* cpu_baseline  the reference's own CPU code (oracle/_ref) on this box's host cores, bounded sample
+
+--impl reference times the reference CPU implementation instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 3840, 2160
+QUANT = dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=8, profile=2, bitDepth=12, preScaling=1.0,
+             maxLum=1e4, minLum=0.005)
+BYTES_PER_PX_PASS = 15.0  # 12 B f32 RGB + 2 B Y + 2 * 2 B / 4 chroma, either direction
+WORKLOAD = "4K (3840x2160) f32 RGB, PQ, Lu'v' 11/8-bit, profile 2 (4:2:0 LE16): encode+decode round trip"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=4, help="frames per GPU per end-to-end step")
+    ap.add_argument("--cpu-frames", type=int, default=1, help="frames per worker in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_baseline(frames_per_worker: int, workers: int | None = None) -> dict:
+    """The reference's CPU path in a separate process tree (never shares a process with CUDA)."""
+    workers = workers or host_cores()
+    cmd = [sys.executable, str(ROOT / "oracle" / "cpu_baseline.py"), "--workers", str(workers), "--frames",
+           str(frames_per_worker), "--width", str(W), "--height", str(H)]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    return json.loads(out)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = None
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = run_cpu_baseline(args.cpu_frames)
+        if i >= args.warmup:
+            times.append((time.perf_counter() - t0, res))
+    vals = sorted(r["value"] for _, r in times)
+    value = vals[len(vals) // 2]
+    px_per_step = res["cores"] * args.cpu_frames * W * H
+    line = {
+        "impl": "reference", "metric": "Mpixels/s encode+decode (PQ Lu'v' 4K float32)", "value": value,
+        "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": px_per_step / value / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": res["cores"] * args.cpu_frames,
+                   "note": "reference CPU implementation (LumaEncoder::encode + LumaDecoder::decode, VP9 stubbed out), "
+                           "one independent frame stream per host core"},
+        "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"], "per_core_mpx_s": res["per_core_mpx_s"]},
+        "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ours_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import lumahdrv_b200 as L
+    from lumahdrv_b200.device import DeviceTransform
+    from lumahdrv_b200.shard import broadcast_quantizer, frame_shard, pack_quantizer, unpack_quantizer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the transform has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_baseline(args.cpu_frames)
+
+    # ---- quantizer: rank 0 builds the LUT with its libm, everyone receives it (the only collective)
+    n_lut = 1 << QUANT["ptfBitDepth"]
+    if world > 1:
+        vec = None
+        if rank == 0:
+            lut = L.build_lut(QUANT["ptf"], QUANT["ptfBitDepth"], QUANT["maxLum"], QUANT["minLum"])
+            vec = pack_quantizer(lut, (1 << QUANT["colorBitDepth"]) - 1, L.CS_LUV, QUANT["maxLum"], QUANT["minLum"],
+                                 QUANT["preScaling"], QUANT["profile"])
+        got = unpack_quantizer(broadcast_quantizer(vec, 7 + n_lut, dev, src=0))
+        shared_lut = got["lut"]
+    else:
+        shared_lut = None
+    t = DeviceTransform(local, ptf=QUANT["ptf"], ptfBitDepth=QUANT["ptfBitDepth"], colorSpace=QUANT["colorSpace"],
+                        colorBitDepth=QUANT["colorBitDepth"], maxLum=QUANT["maxLum"], minLum=QUANT["minLum"],
+                        profile=QUANT["profile"], preScaling=QUANT["preScaling"], lut=shared_lut)
+
+    # ---- this rank's shard of the synthetic frame stream (weak scaling: F frames per GPU per step)
+    F = args.frames
+    mine = frame_shard(F * world, rank, world)
+    rgb = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
+    for i, gidx in enumerate(mine):
+        g = torch.Generator(device=dev).manual_seed(0x9E3779B9 + gidx)
+        u = torch.rand((3, H, W), generator=g, device=dev, dtype=torch.float32)
+        rgb[i] = 0.005 * torch.pow(torch.tensor(2.0e6, device=dev), u)  # log-uniform 0.005 .. 1e4 cd/m2
+    planes = t.alloc_planes(F, W, H)
+    out = torch.empty_like(rgb)
+    stats = t.alloc_stats(F)
+    torch.cuda.synchronize()
+
+    def step():
+        t.encode(rgb, planes=planes, stats=stats)
+        t.decode(planes, W, H, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, per-kernel events inside
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = t.launch_count
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record()
+        t.encode(rgb, planes=planes, stats=stats)
+        ev[k][1].record()
+        t.decode(planes, W, H, out=out)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = t.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    tt = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = (float(v) for v in tt.tolist())
+    px_step = F * W * H  # per GPU
+    value = world * px_step * args.steps / (total_ms / 1e3) / 1e6
+
+    # sanity: the timed work really produced the round trip (compare one frame with the input scale)
+    st = t.stats_to_numpy(stats)
+    assert np.all(np.isfinite(st["sum"])) and np.all(st["sum"] > 0)
+
+    # ---- end to end through the host-pointer C ABI, pinned host memory, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Fe = args.e2e_frames
+        h_in = torch.empty((Fe, 3, H, W), dtype=torch.float32).pin_memory()
+        h_in.copy_(rgb[:Fe].cpu())
+        h_out = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+        strides = L.vpx_strides(W, QUANT["profile"])
+        h_planes = [torch.empty((ph, s), dtype=torch.uint8).pin_memory()
+                    for (pw, ph), s in zip(L.plane_dims(W, H, QUANT["profile"]), strides)]
+        enc = L.LumaEncoder(local)
+        enc.setParams(L.LumaEncoderParams(**{k: QUANT[k] for k in ("ptfBitDepth", "colorBitDepth", "preScaling", "minLum",
+                                                                     "maxLum", "profile", "bitDepth")},
+                                          ptf=L.PTF_PQ, colorSpace=L.CS_LUV))
+        enc.initialize(None, W, H)
+        dec = L.LumaDecoder(local)
+        dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=L.CS_LUV, ptfBitDepth=QUANT["ptfBitDepth"],
+                                          colorBitDepth=QUANT["colorBitDepth"], profile=QUANT["profile"]))
+        dec.initialize()
+        dec.m_frame = h_out.numpy()
+        np_in = h_in.numpy()
+        np_planes = [p.numpy() for p in h_planes]
+
+        def e2e_step():
+            for i in range(Fe):
+                enc.encode(np_in[i], np_planes)      # H2D 12 B/px, kernel, D2H 3 B/px
+                dec.decode(np_planes, W, H)          # H2D 3 B/px, kernel, D2H 12 B/px
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        l0 = enc.m_quant.ctx.launch_count + dec.m_quant.ctx.launch_count
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_launches = enc.m_quant.ctx.launch_count + dec.m_quant.ctx.launch_count - l0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        plane_bytes = sum(pw * ph * 2 for pw, ph in L.plane_dims(W, H, QUANT["profile"]))
+        e2e = {"value": world * Fe * W * H * e2e_steps / dt / 1e6, "unit": "Mpixels/s",
+               "h2d_bytes_per_step": Fe * (12 * W * H + plane_bytes), "d2h_bytes_per_step": Fe * (12 * W * H + plane_bytes),
+               "steps": e2e_steps, "frames_per_step": Fe, "gpu_launches": e2e_launches,
+               "api": "lumacu_encode + lumacu_decode (host pointers, pinned), via LumaEncoder.encode / LumaDecoder.decode"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        bytes_pass = BYTES_PER_PX_PASS * px_step
+        dom = "encode_kernel" if enc_ms >= dec_ms else "decode_kernel"
+        dom_ms = max(enc_ms, dec_ms)
+        achieved = bytes_pass / (dom_ms / 1e3) / 1e9
+        line = {
+            "metric": "Mpixels/s encode+decode (PQ Lu'v' 4K float32)", "value": value, "unit": "Mpixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F,
+                       "input": "seeded log-uniform noise 0.005..1e4 cd/m2, distinct per frame",
+                       "l2": f"inputs larger than L2: {F * (12 + 3 + 12) * W * H / 1e6:.0f} MB touched per step per GPU vs 126 MB L2",
+                       "parallelism": f"frame shards x{world}, LUT broadcast only"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": bytes_pass, "kernel_ms": dom_ms,
+                         "encode_ms": enc_ms, "decode_ms": dec_ms,
+                         "encode_gbs": bytes_pass / (enc_ms / 1e3) / 1e9, "decode_gbs": bytes_pass / (dec_ms / 1e3) / 1e9,
+                         "round_trip_frac_of_peak": (2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9) / peak,
+                         "frac_of_nominal_8tbs": (2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9) / 8000.0},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": "Mpixels/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                    "sample": cpu["sample"], "per_core_mpx_s": cpu["per_core_mpx_s"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,9 @@ typedef struct lumacu_ctx lumacu_ctx;
 int lumacu_version(void);
 const char *lumacu_status_name(int status);
 int lumacu_device_count(int *count);
+/* 1 when the PSI / JND-HDR-VDP tables (reference include/luma/ptfs/, consumed at
+ * build time) were compiled in, 0 otherwise. */
+int lumacu_have_ptf_tables(void);
 
 /* Creates a context bound to CUDA device `device` (own stream, pinned staging
  * buffers grown on demand).  Replaces nothing in the reference; it is the state
@@ -98,6 +101,13 @@ const char *lumacu_last_error(const lumacu_ctx *ctx);
 int lumacu_device(const lumacu_ctx *ctx);
 /* Block until all work queued on the context's own stream has finished. */
 int lumacu_synchronize(lumacu_ctx *ctx);
+/* The context's own cudaStream_t (as void*). */
+void *lumacu_stream(lumacu_ctx *ctx);
+/* Page-locked host memory for frames / planes handed to the host-pointer entry
+ * points (what LumaFrame::buffer and the vpx image planes should live in for
+ * full PCIe rate).  Not tied to a context. */
+int lumacu_host_alloc(size_t bytes, void **out);
+int lumacu_host_free(void *p);
 
 /* ---- quantizer -------------------------------------------------------------- */
 /* Host-side LUT construction = the table half of LumaQuantizer::setQuantizer
@@ -107,6 +117,21 @@ int lumacu_synchronize(lumacu_ctx *ctx);
  * (powf/log10f) the reference uses. */
 int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out,
                      size_t cap);
+
+/* Host-side analysis of LumaQuantizer::quantize's luma branch
+ * (src/luma_quantizer.cpp:219-235).  For a finite, strictly increasing LUT the
+ * reference's "bisect, then pick the nearer neighbour with fp32 differences" is
+ * a monotone step function of val; thr_keys[k-1] receives the order-preserving
+ * integer key (sign-magnitude -> unsigned) of the smallest float whose code is
+ * >= k, for k = 1 .. lut_len-1.  Returns 1 on success, 0 when the LUT is not
+ * finite/strictly increasing (the kernels then replay the reference loop
+ * literally).  Pure host code; exposed so that tests can pin the thresholds
+ * against the oracle without a GPU. */
+int lumacu_derive_thresholds(const float *lut, uint32_t lut_len, uint32_t *thr_keys);
+/* Bucket table geometry chosen for a threshold list: bucket = key >> shift,
+ * table covers [base, base + n_buckets), walk = max thresholds per bucket. */
+int lumacu_plan_buckets(const uint32_t *thr_keys, uint32_t n_thr, uint32_t *shift, uint32_t *base,
+                        uint32_t *n_buckets, uint32_t *walk);
 
 /* Device-side quantizer state = the fields LumaQuantizer keeps
  * (include/luma/luma_quantizer.h:120-126): the code->luminance LUT
@@ -173,8 +198,9 @@ int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size
 /* Number of kernels this context has launched so far. */
 uint64_t lumacu_launch_count(const lumacu_ctx *ctx);
 /* Describes how the luma search was configured by the last set_quantizer:
- * mode 0 = bucket table + threshold walk in shared memory, 1 = exact binary
- * search replica in global memory. */
+ * mode 0 = bucket table + threshold walk (shared memory), 1 = binary search
+ * over the thresholds, 2 = literal replica of the reference's bisection over
+ * the LUT (LUT not strictly increasing). */
 int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift,
                        uint32_t *walk);
 

@@ -1,0 +1,612 @@
+/*
+ * luma_kernels.cuh -- the fused sm_100a kernels of the HDR<->integer transform.
+ *
+ *   encode_kernel : planar f32 RGB -> {colour transform -> luma LUT search |
+ *                   chroma 2x2 mean -> round/clamp} -> pitched u8 / LE-u16 planes
+ *                   (+ per-frame sum/max/min of plane 0), one pass over HBM.
+ *                   Replaces LumaQuantizer::transformColorSpace(frame,true,sc)
+ *                   + LumaEncoder::setVpxChannel x3 (reference
+ *                   src/luma_quantizer.cpp:269-373, src/luma_encoder.cpp:260-317).
+ *   decode_kernel : pitched planes -> LUT gather / chroma scale -> 2x2 replicate
+ *                   -> inverse colour -> planar f32 RGB.  Replaces
+ *                   LumaDecoder::getVpxChannels + transformColorSpace(frame,false,sc)
+ *                   (src/luma_decoder.cpp:205-240, src/luma_quantizer.cpp:374-479).
+ *
+ * Work decomposition: one thread owns a 2-row x 4-column pixel tile, so a 4:2:0
+ * chroma block (2x2) is thread-local, each row-plane access of a warp is one
+ * contiguous 512 B (f32) / 256 B (u16) segment, and all global accesses are
+ * 128/64/32-bit vectors.  Blocks are persistent (grid-stride over tiles) so the
+ * search tables are staged into shared memory once per block.
+ */
+#pragma once
+
+#include "luma_device.cuh"
+
+namespace lumacu {
+
+constexpr int kThreads = 256;
+
+struct StatsPartial {
+    double sum;
+    float mx;
+    float mn;
+};
+
+struct FrameStatsDev { /* same layout as lumacu_frame_stats */
+    double sum;
+    float mx;
+    float mn;
+};
+
+struct EncArgs {
+    QuantDev q;
+    const float *rgb;
+    float *rgb_out; /* nullable: colour-transformed frame (reference's in-place side effect) */
+    size_t rgb_plane_stride; /* floats between the R, G, B planes */
+    size_t rgb_frame_stride; /* floats between frames */
+    size_t out_plane_stride, out_frame_stride;
+    uint32_t w, h;
+    uint8_t *plane[3];
+    int32_t stride[3];
+    size_t plane_frame_stride[3];
+    float sc;
+    int prescale; /* sc != 1 */
+    StatsPartial *partial; /* [frames][gridDim.x], nullable together with stats */
+    uint32_t *counter;     /* [frames] */
+    FrameStatsDev *stats;  /* [frames] */
+};
+
+struct DecArgs {
+    QuantDev q;
+    const uint8_t *plane[3];
+    int32_t stride[3];
+    size_t plane_frame_stride[3];
+    float *rgb;
+    size_t rgb_plane_stride;
+    size_t rgb_frame_stride;
+    uint32_t w, h;
+    float sc;
+    int prescale;
+};
+
+/* ---- streaming global accesses (each byte is touched once) --------------------- */
+__device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+/* Stage the search tables (thresholds + bucket heads) into shared memory. */
+__device__ __forceinline__ SearchCtx make_search_ctx(const QuantDev &q, unsigned char *smem)
+{
+    SearchCtx s;
+    s.lut = q.lut;
+    s.max_val = q.max_val;
+    s.shift = q.shift;
+    s.base = q.base;
+    s.nbm1 = q.nbm1;
+    s.walk = q.walk;
+    s.mode = q.search_mode;
+    s.thr = q.thr;
+    s.bucket = q.bucket;
+    if (q.smem_tables) {
+        uint32_t *thr_s = reinterpret_cast<uint32_t *>(smem);
+        for (uint32_t i = threadIdx.x; i < q.thr_count; i += blockDim.x)
+            thr_s[i] = q.thr[i];
+        s.thr = thr_s;
+        if (q.search_mode == SEARCH_BUCKET) {
+            /* bucket heads are u16; copy them as u32 pairs (table is padded to an even count) */
+            uint32_t *b_s = thr_s + q.thr_count;
+            const uint32_t *b_g = reinterpret_cast<const uint32_t *>(q.bucket);
+            const uint32_t n32 = (q.nbm1 + 2) >> 1;
+            for (uint32_t i = threadIdx.x; i < n32; i += blockDim.x)
+                b_s[i] = b_g[i];
+            s.bucket = reinterpret_cast<const uint16_t *>(b_s);
+        }
+        __syncthreads();
+    }
+    return s;
+}
+
+__device__ __forceinline__ void atomic_noop() {}
+
+/* Block-wide reduction of the per-thread plane-0 statistics; the last block of a
+ * frame folds all block partials in a fixed order (deterministic result). */
+__device__ __forceinline__ void finish_stats(const EncArgs &a, uint32_t frame, double sum, float mx, float mn)
+{
+    __shared__ double s_sum[kThreads / 32];
+    __shared__ float s_mx[kThreads / 32];
+    __shared__ float s_mn[kThreads / 32];
+    __shared__ uint32_t s_last;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) {
+        s_sum[warp] = sum;
+        s_mx[warp] = mx;
+        s_mn[warp] = mn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; ++i) {
+            sum += s_sum[i];
+            mx = fmaxf(mx, s_mx[i]);
+            mn = fminf(mn, s_mn[i]);
+        }
+        StatsPartial p;
+        p.sum = sum;
+        p.mx = mx;
+        p.mn = mn;
+        a.partial[(size_t)frame * gridDim.x + blockIdx.x] = p;
+        __threadfence();
+        s_last = (atomicAdd(&a.counter[frame], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        double t = 0.0;
+        float tx = -INFINITY, tn = INFINITY;
+        const volatile StatsPartial *pp = a.partial + (size_t)frame * gridDim.x;
+        for (uint32_t i = lane; i < gridDim.x; i += 32) {
+            t += pp[i].sum;
+            tx = fmaxf(tx, pp[i].mx);
+            tn = fminf(tn, pp[i].mn);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_down_sync(0xffffffffu, t, o);
+            tx = fmaxf(tx, __shfl_down_sync(0xffffffffu, tx, o));
+            tn = fminf(tn, __shfl_down_sync(0xffffffffu, tn, o));
+        }
+        if (lane == 0) {
+            a.stats[frame].sum = t;
+            a.stats[frame].mx = tx;
+            a.stats[frame].mn = tn;
+            a.counter[frame] = 0; /* self-cleaning for the next launch */
+        }
+    }
+}
+
+/* pack four codes of one row into the plane's sample container */
+template <int BYTES>
+__device__ __forceinline__ void store_codes4(uint8_t *row, uint32_t x, const uint32_t c[4], bool vec, uint32_t nvalid)
+{
+    if (BYTES == 2) {
+        if (vec) {
+            uint2 v;
+            v.x = (c[0] & 0xffffu) | (c[1] << 16);
+            v.y = (c[2] & 0xffffu) | (c[3] << 16);
+            __stcs(reinterpret_cast<uint2 *>(row + 2 * (size_t)x), v);
+        } else {
+            for (uint32_t i = 0; i < nvalid; ++i) {
+                row[2 * (size_t)(x + i)] = (uint8_t)(c[i] & 0xffu);
+                row[2 * (size_t)(x + i) + 1] = (uint8_t)((c[i] >> 8) & 0xffu);
+            }
+        }
+    } else {
+        if (vec) {
+            uint32_t v = (c[0] & 0xffu) | ((c[1] & 0xffu) << 8) | ((c[2] & 0xffu) << 16) | (c[3] << 24);
+            __stcs(reinterpret_cast<uint32_t *>(row + x), v);
+        } else {
+            for (uint32_t i = 0; i < nvalid; ++i)
+                row[x + i] = (uint8_t)(c[i] & 0xffu);
+        }
+    }
+}
+
+template <int BYTES>
+__device__ __forceinline__ void store_codes2(uint8_t *row, uint32_t x, const uint32_t c[2], bool vec, uint32_t nvalid)
+{
+    if (BYTES == 2) {
+        if (vec) {
+            __stcs(reinterpret_cast<uint32_t *>(row + 2 * (size_t)x), (c[0] & 0xffffu) | (c[1] << 16));
+        } else {
+            for (uint32_t i = 0; i < nvalid; ++i) {
+                row[2 * (size_t)(x + i)] = (uint8_t)(c[i] & 0xffu);
+                row[2 * (size_t)(x + i) + 1] = (uint8_t)((c[i] >> 8) & 0xffu);
+            }
+        }
+    } else {
+        if (vec) {
+            *reinterpret_cast<uint16_t *>(row + x) = (uint16_t)((c[0] & 0xffu) | ((c[1] & 0xffu) << 8));
+        } else {
+            for (uint32_t i = 0; i < nvalid; ++i)
+                row[x + i] = (uint8_t)(c[i] & 0xffu);
+        }
+    }
+}
+
+template <int BYTES>
+__device__ __forceinline__ void load_codes4(const uint8_t *row, uint32_t x, uint32_t c[4], bool vec, uint32_t nvalid)
+{
+    if (BYTES == 2) {
+        if (vec) {
+            uint2 v = __ldcs(reinterpret_cast<const uint2 *>(row + 2 * (size_t)x));
+            c[0] = v.x & 0xffffu;
+            c[1] = v.x >> 16;
+            c[2] = v.y & 0xffffu;
+            c[3] = v.y >> 16;
+        } else {
+            for (uint32_t i = 0; i < 4; ++i)
+                c[i] = (i < nvalid) ? ((uint32_t)row[2 * (size_t)(x + i)] | ((uint32_t)row[2 * (size_t)(x + i) + 1] << 8))
+                                    : 0u;
+        }
+    } else {
+        if (vec) {
+            uint32_t v = __ldcs(reinterpret_cast<const uint32_t *>(row + x));
+            c[0] = v & 0xffu;
+            c[1] = (v >> 8) & 0xffu;
+            c[2] = (v >> 16) & 0xffu;
+            c[3] = v >> 24;
+        } else {
+            for (uint32_t i = 0; i < 4; ++i)
+                c[i] = (i < nvalid) ? (uint32_t)row[x + i] : 0u;
+        }
+    }
+}
+
+template <int BYTES>
+__device__ __forceinline__ void load_codes2(const uint8_t *row, uint32_t x, uint32_t c[2], bool vec, uint32_t nvalid)
+{
+    if (BYTES == 2) {
+        if (vec) {
+            uint32_t v = __ldcs(reinterpret_cast<const uint32_t *>(row + 2 * (size_t)x));
+            c[0] = v & 0xffffu;
+            c[1] = v >> 16;
+        } else {
+            for (uint32_t i = 0; i < 2; ++i)
+                c[i] = (i < nvalid) ? ((uint32_t)row[2 * (size_t)(x + i)] | ((uint32_t)row[2 * (size_t)(x + i) + 1] << 8))
+                                    : 0u;
+        }
+    } else {
+        if (vec) {
+            uint32_t v = __ldcs(reinterpret_cast<const uint16_t *>(row + x));
+            c[0] = v & 0xffu;
+            c[1] = (v >> 8) & 0xffu;
+        } else {
+            for (uint32_t i = 0; i < 2; ++i)
+                c[i] = (i < nvalid) ? (uint32_t)row[x + i] : 0u;
+        }
+    }
+}
+
+/* =============================== encode ========================================= */
+template <int CS, bool SUB, int BYTES, bool VEC>
+__global__ void __launch_bounds__(kThreads) encode_kernel(const EncArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SearchCtx s = make_search_ctx(a.q, smem_raw);
+    constexpr bool LUT_ALL = (CS == CS_RGB || CS == CS_XYZ); /* every plane goes through the LUT search */
+    constexpr bool POS = (CS == CS_LUV || CS == CS_XYZ);     /* searched values are > 0 or canonical NaN */
+
+    const uint32_t frame = blockIdx.y;
+    const float *rgb = a.rgb + (size_t)frame * a.rgb_frame_stride;
+    float *rgb_out = a.rgb_out ? a.rgb_out + (size_t)frame * a.out_frame_stride : nullptr;
+    uint8_t *pl0 = a.plane[0] + (size_t)frame * a.plane_frame_stride[0];
+    uint8_t *pl1 = a.plane[1] + (size_t)frame * a.plane_frame_stride[1];
+    uint8_t *pl2 = a.plane[2] + (size_t)frame * a.plane_frame_stride[2];
+    const uint32_t w = a.w, h = a.h;
+    const float max_c = a.q.max_val_color_f;
+    const float l_max = a.q.l_max;
+
+    const uint32_t tpr = (w + 3) >> 2;
+    const uint32_t ntiles = tpr * ((h + 1) >> 1);
+
+    double sum = 0.0;
+    float mx = -INFINITY, mn = INFINITY;
+
+    for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < ntiles; t += gridDim.x * kThreads) {
+        const uint32_t ty = t / tpr;
+        const uint32_t x0 = (t - ty * tpr) * 4u, y0 = ty * 2u;
+        const uint32_t nx = VEC ? 4u : min(4u, w - x0);
+        const uint32_t ny = VEC ? 2u : min(2u, h - y0);
+
+        float c[3][2][4];
+        /* ---- load: 6 x 128-bit per thread, contiguous 512 B per warp and row-plane */
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float *src = rgb + (size_t)p * a.rgb_plane_stride + (size_t)(y0 + r) * w + x0;
+                if (VEC) {
+                    float4 v = ld_stream4(src);
+                    c[p][r][0] = v.x;
+                    c[p][r][1] = v.y;
+                    c[p][r][2] = v.z;
+                    c[p][r][3] = v.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c[p][r][i] = ((uint32_t)r < ny && (uint32_t)i < nx) ? src[i] : 1.0f;
+                }
+            }
+        }
+
+        /* ---- colour transform, per pixel */
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float R = c[0][r][i], G = c[1][r][i], B = c[2][r][i];
+                if (a.prescale) {
+                    R = __fmul_rn(R, a.sc);
+                    G = __fmul_rn(G, a.sc);
+                    B = __fmul_rn(B, a.sc);
+                }
+                color_forward<CS>(R, G, B, l_max, c[0][r][i], c[1][r][i], c[2][r][i]);
+            }
+        }
+
+        /* ---- optional write-back of the transformed frame (reference side effect) */
+        if (rgb_out) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    float *dst = rgb_out + (size_t)p * a.out_plane_stride + (size_t)(y0 + r) * w + x0;
+                    if (VEC) {
+                        st_stream4(dst, make_float4(c[p][r][0], c[p][r][1], c[p][r][2], c[p][r][3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((uint32_t)r < ny && (uint32_t)i < nx)
+                                dst[i] = c[p][r][i];
+                    }
+                }
+            }
+        }
+
+        /* ---- plane-0 statistics (src/luma_encoder.cpp:276,294,314-316) */
+        if (a.stats) {
+            float part[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (VEC) {
+                    part[r] = (c[0][r][0] + c[0][r][1]) + (c[0][r][2] + c[0][r][3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        mx = fmaxf(mx, c[0][r][i]);
+                        mn = fminf(mn, c[0][r][i]);
+                    }
+                } else {
+                    part[r] = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((uint32_t)r < ny && (uint32_t)i < nx) {
+                            part[r] += c[0][r][i];
+                            mx = fmaxf(mx, c[0][r][i]);
+                            mn = fminf(mn, c[0][r][i]);
+                        }
+                }
+            }
+            sum += (double)part[0] + (double)part[1];
+        }
+
+        /* ---- plane 0: LUT search, pack, store */
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t code[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                code[i] = search_code<POS>(s, c[0][r][i]);
+            if (VEC || (uint32_t)r < ny)
+                store_codes4<BYTES>(pl0 + (size_t)(y0 + r) * a.stride[0], x0, code, VEC, nx);
+        }
+
+        /* ---- planes 1, 2 */
+        if (SUB) {
+#pragma unroll
+            for (int p = 1; p < 3; ++p) {
+                uint32_t code[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    /* 0.25f*(((a+b)+c)+d), src/luma_encoder.cpp:287-290 */
+                    float m = __fmul_rn(
+                        0.25f, __fadd_rn(__fadd_rn(__fadd_rn(c[p][0][2 * j], c[p][0][2 * j + 1]), c[p][1][2 * j]),
+                                         c[p][1][2 * j + 1]));
+                    code[j] = LUT_ALL ? search_code<POS>(s, m) : quantize_chroma(m, max_c);
+                }
+                uint8_t *row = (p == 1 ? pl1 : pl2) + (size_t)ty * a.stride[p];
+                store_codes2<BYTES>(row, x0 >> 1, code, VEC, (nx + 1) >> 1);
+            }
+        } else {
+#pragma unroll
+            for (int p = 1; p < 3; ++p) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    uint32_t code[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        code[i] = LUT_ALL ? search_code<POS>(s, c[p][r][i]) : quantize_chroma(c[p][r][i], max_c);
+                    if (VEC || (uint32_t)r < ny)
+                        store_codes4<BYTES>((p == 1 ? pl1 : pl2) + (size_t)(y0 + r) * a.stride[p], x0, code, VEC, nx);
+                }
+            }
+        }
+    }
+
+    if (a.stats)
+        finish_stats(a, frame, sum, mx, mn);
+}
+
+/* =============================== decode ========================================= */
+template <int CS, bool SUB, int BYTES, bool VEC>
+__global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool LUT_ALL = (CS == CS_RGB || CS == CS_XYZ);
+
+    const float *lut = a.q.lut;
+    if (a.q.smem_lut) {
+        float *lut_s = reinterpret_cast<float *>(smem_raw);
+        for (uint32_t i = threadIdx.x; i <= a.q.max_val; i += blockDim.x)
+            lut_s[i] = a.q.lut[i];
+        __syncthreads();
+        lut = lut_s;
+    }
+
+    const uint32_t frame = blockIdx.y;
+    const uint8_t *pl0 = a.plane[0] + (size_t)frame * a.plane_frame_stride[0];
+    const uint8_t *pl1 = a.plane[1] + (size_t)frame * a.plane_frame_stride[1];
+    const uint8_t *pl2 = a.plane[2] + (size_t)frame * a.plane_frame_stride[2];
+    float *rgb = a.rgb + (size_t)frame * a.rgb_frame_stride;
+    const uint32_t w = a.w, h = a.h;
+    const uint32_t max_val = a.q.max_val;
+    const float max_c = a.q.max_val_color_f;
+    const float l_max = a.q.l_max;
+
+    const uint32_t tpr = (w + 3) >> 2;
+    const uint32_t ntiles = tpr * ((h + 1) >> 1);
+
+    for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < ntiles; t += gridDim.x * kThreads) {
+        const uint32_t ty = t / tpr;
+        const uint32_t x0 = (t - ty * tpr) * 4u, y0 = ty * 2u;
+        const uint32_t nx = VEC ? 4u : min(4u, w - x0);
+        const uint32_t ny = VEC ? 2u : min(2u, h - y0);
+
+        uint32_t code0[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (VEC || (uint32_t)r < ny)
+                load_codes4<BYTES>(pl0 + (size_t)(y0 + r) * a.stride[0], x0, code0[r], VEC, nx);
+            else
+                code0[r][0] = code0[r][1] = code0[r][2] = code0[r][3] = 0u;
+        }
+
+        /* chroma: one ChromaInv per 2x2 block (SUB) or per pixel */
+        ChromaInv chr[2][4];
+        if (SUB) {
+            uint32_t cc[2][2];
+            load_codes2<BYTES>(pl1 + (size_t)ty * a.stride[1], x0 >> 1, cc[0], VEC, (nx + 1) >> 1);
+            load_codes2<BYTES>(pl2 + (size_t)ty * a.stride[2], x0 >> 1, cc[1], VEC, (nx + 1) >> 1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float c1, c2;
+                if (LUT_ALL) {
+                    c1 = lut[min(cc[0][j], max_val)];
+                    c2 = lut[min(cc[1][j], max_val)];
+                } else {
+                    c1 = dequantize_chroma((float)cc[0][j], max_c);
+                    c2 = dequantize_chroma((float)cc[1][j], max_c);
+                }
+                ChromaInv ci = chroma_inverse<CS>(c1, c2);
+                chr[0][2 * j] = chr[0][2 * j + 1] = chr[1][2 * j] = chr[1][2 * j + 1] = ci;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                uint32_t cc1[4] = {0u, 0u, 0u, 0u}, cc2[4] = {0u, 0u, 0u, 0u};
+                if (VEC || (uint32_t)r < ny) {
+                    load_codes4<BYTES>(pl1 + (size_t)(y0 + r) * a.stride[1], x0, cc1, VEC, nx);
+                    load_codes4<BYTES>(pl2 + (size_t)(y0 + r) * a.stride[2], x0, cc2, VEC, nx);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float c1, c2;
+                    if (LUT_ALL) {
+                        c1 = lut[min(cc1[i], max_val)];
+                        c2 = lut[min(cc2[i], max_val)];
+                    } else {
+                        c1 = dequantize_chroma((float)cc1[i], max_c);
+                        c2 = dequantize_chroma((float)cc2[i], max_c);
+                    }
+                    chr[r][i] = chroma_inverse<CS>(c1, c2);
+                }
+            }
+        }
+
+        float o[3][2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float c0 = lut[min(code0[r][i], max_val)];
+                float R, G, B;
+                color_inverse<CS>(c0, chr[r][i], l_max, R, G, B);
+                if (a.prescale) {
+                    R = __fdiv_rn(R, a.sc);
+                    G = __fdiv_rn(G, a.sc);
+                    B = __fdiv_rn(B, a.sc);
+                }
+                o[0][r][i] = R;
+                o[1][r][i] = G;
+                o[2][r][i] = B;
+            }
+        }
+
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float *dst = rgb + (size_t)p * a.rgb_plane_stride + (size_t)(y0 + r) * w + x0;
+                if (VEC) {
+                    st_stream4(dst, make_float4(o[p][r][0], o[p][r][1], o[p][r][2], o[p][r][3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((uint32_t)r < ny && (uint32_t)i < nx)
+                            dst[i] = o[p][r][i];
+                }
+            }
+        }
+    }
+}
+
+/* ====================== element-wise API kernels ================================= */
+/* LumaQuantizer::transformColorSpace in place on a planar frame of n pixels. */
+template <int CS, bool FWD>
+__global__ void __launch_bounds__(kThreads) transform_kernel(float *c0, float *c1, float *c2, size_t n, float sc, float l_max)
+{
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        float a = c0[i], b = c1[i], c = c2[i];
+        float x, y, z;
+        if (FWD) {
+            color_forward<CS>(__fmul_rn(a, sc), __fmul_rn(b, sc), __fmul_rn(c, sc), l_max, x, y, z);
+        } else {
+            ChromaInv ci = chroma_inverse<CS>(b, c);
+            color_inverse<CS>(a, ci, l_max, x, y, z);
+            x = __fdiv_rn(x, sc);
+            y = __fdiv_rn(y, sc);
+            z = __fdiv_rn(z, sc);
+        }
+        c0[i] = x;
+        c1[i] = y;
+        c2[i] = z;
+    }
+}
+
+/* LumaQuantizer::quantize over an array (codes returned as floats). */
+__global__ void __launch_bounds__(kThreads) quantize_kernel(const QuantDev q, const float *in, float *out, size_t n, int use_lut)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SearchCtx s = make_search_ctx(q, smem_raw);
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float v = in[i];
+        out[i] = use_lut ? (float)search_code<false>(s, v) : (float)quantize_chroma(v, q.max_val_color_f);
+    }
+}
+
+/* LumaQuantizer::dequantize over an array (src/luma_quantizer.cpp:247-264). */
+__global__ void __launch_bounds__(kThreads) dequantize_kernel(const QuantDev q, const float *in, float *out, size_t n, int use_lut)
+{
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float v = in[i];
+        float r;
+        if (use_lut) {
+            if (v < 0.0f)
+                r = q.lut[0];
+            else if (v >= q.max_val_f)
+                r = q.lut[q.max_val];
+            else if (v == v)
+                r = q.lut[(int)v];
+            else
+                r = q.lut[0]; /* NaN index: undefined behaviour in the reference; pinned to entry 0 here */
+        } else {
+            r = dequantize_chroma(v, q.max_val_color_f);
+        }
+        out[i] = r;
+    }
+}
+
+} // namespace lumacu

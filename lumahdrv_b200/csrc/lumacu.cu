@@ -1,0 +1,997 @@
+/*
+ * lumacu.cu -- C ABI (include/lumacu.h) over the sm_100a kernels.
+ *
+ * Host responsibilities kept here:
+ *   - LUT construction with the host libm, exactly as
+ *     LumaQuantizer::setQuantizer does (reference src/luma_quantizer.cpp:172-212);
+ *   - derivation of the exact decision thresholds of LumaQuantizer::quantize
+ *     (src/luma_quantizer.cpp:219-235) and of the bucket table that turns the
+ *     reference's 11-step bisection into one table read plus <= `walk` compares;
+ *   - launch configuration (persistent grid = SM count x resident blocks),
+ *     staging for the host-pointer entry points, error reporting.
+ * There is no CPU implementation of the transform in this library: without a
+ * CUDA device every compute entry point fails with LUMACU_ERR_NO_DEVICE/_CUDA.
+ */
+#include "../../include/lumacu.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "luma_kernels.cuh"
+
+using namespace lumacu;
+
+#ifdef LUMA_HAVE_PTF_TABLES
+/* Constant perceptual-transfer-function tables are consumed from the reference
+ * checkout at build time (include/luma/luma_quantizer.h:55-77): data, not code. */
+static const float k_ptf_psi_10[] = {
+#include "ptfs/ptf_jnd_ferwerda_10bit.h"
+};
+static const float k_ptf_psi_11[] = {
+#include "ptfs/ptf_jnd_ferwerda_11bit.h"
+};
+static const float k_ptf_psi_12[] = {
+#include "ptfs/ptf_jnd_ferwerda_12bit.h"
+};
+static const float k_ptf_vdp_10[] = {
+#include "ptfs/ptf_jnd_hdrvdp_10bit.h"
+};
+static const float k_ptf_vdp_11[] = {
+#include "ptfs/ptf_jnd_hdrvdp_11bit.h"
+};
+static const float k_ptf_vdp_12[] = {
+#include "ptfs/ptf_jnd_hdrvdp_12bit.h"
+};
+#endif
+
+namespace {
+
+constexpr uint32_t kMaxBuckets = 8192; /* u16 heads: <= 16 KB of shared memory */
+constexpr uint32_t kMaxWalk = 8;
+constexpr size_t kMaxSmemTables = 96 * 1024;
+constexpr size_t kMaxSmemLut = 64 * 1024;
+
+thread_local std::string g_create_error;
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct lumacu_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    std::string err;
+    uint64_t launches = 0;
+
+    /* quantizer */
+    bool configured = false;
+    int color_space = 0;
+    QuantDev q{};
+    std::vector<float> h_lut;
+    DeviceBuffer d_tables; /* lut | thr | bucket */
+    size_t smem_enc = 0, smem_dec = 0;
+
+    /* stats workspace */
+    DeviceBuffer d_partial, d_counter;
+
+    /* staging for the host-pointer entry points */
+    DeviceBuffer d_rgb, d_planes, d_stats, d_aux;
+    void *h_pin = nullptr;
+    size_t h_pin_cap = 0;
+};
+
+namespace {
+
+int fail(lumacu_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? LUMACU_ERR_OUT_OF_MEMORY : LUMACU_ERR_CUDA, \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                         \
+    } while (0)
+
+int reserve(lumacu_ctx *ctx, DeviceBuffer &b, size_t bytes)
+{
+    if (bytes <= b.cap)
+        return LUMACU_OK;
+    if (b.p) {
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    CU_TRY(ctx, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return LUMACU_OK;
+}
+
+/* ---- order-preserving integer key of a float (same mapping as the device) ------ */
+inline uint32_t f2u(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+inline float u2f(uint32_t u)
+{
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+inline uint32_t key_of(float f)
+{
+    uint32_t b = f2u(f);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+inline float float_of_key(uint32_t k)
+{
+    uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return u2f(b);
+}
+
+/* the reference's final decision for the bracket (l, l+1):
+ * "val - m[l] < m[r] - val ? l : r" (src/luma_quantizer.cpp:232) */
+inline bool picks_upper(float val, float ml, float mr)
+{
+    volatile float a = val - ml; /* volatile: keep fp32 rounding, no contraction/excess precision */
+    volatile float b = mr - val;
+    return !(a < b);
+}
+
+} // namespace
+
+/* ================================ host-only helpers ================================= */
+
+extern "C" int lumacu_version(void) { return LUMACU_VERSION; }
+
+extern "C" const char *lumacu_status_name(int status)
+{
+    switch (status) {
+    case LUMACU_OK: return "LUMACU_OK";
+    case LUMACU_ERR_INVALID_ARGUMENT: return "LUMACU_ERR_INVALID_ARGUMENT";
+    case LUMACU_ERR_CUDA: return "LUMACU_ERR_CUDA";
+    case LUMACU_ERR_NOT_CONFIGURED: return "LUMACU_ERR_NOT_CONFIGURED";
+    case LUMACU_ERR_UNSUPPORTED: return "LUMACU_ERR_UNSUPPORTED";
+    case LUMACU_ERR_OUT_OF_MEMORY: return "LUMACU_ERR_OUT_OF_MEMORY";
+    case LUMACU_ERR_NO_DEVICE: return "LUMACU_ERR_NO_DEVICE";
+    default: return "LUMACU_ERR_UNKNOWN";
+    }
+}
+
+extern "C" int lumacu_device_count(int *count)
+{
+    if (!count)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(nullptr, LUMACU_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_have_ptf_tables(void)
+{
+#ifdef LUMA_HAVE_PTF_TABLES
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+/* PQ / log curves with the host libm, float arithmetic as in the reference
+ * (src/luma_quantizer.cpp:485-510; rounded PQ constants narrowed to float). */
+static float host_pq_decode(float val, float L)
+{
+    const float m = 78.8438, n = 0.1593, c1 = 0.8359, c2 = 18.8516, c3 = 18.6875;
+    float Vp = powf(val, 1.0f / m);
+    float num = Vp - c1;
+    num = (0.0f < num) ? num : 0.0f;
+    return L * powf(num / (c2 - c3 * Vp), 1.0f / n);
+}
+
+extern "C" int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out, size_t cap)
+{
+    if (!lut_out || bitdepth > 16)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_build_lut: bad arguments");
+    const unsigned max_val = (unsigned)((int)powf(2.0f, (float)bitdepth) - 1);
+    if (cap < (size_t)max_val + 1)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_build_lut: capacity %zu < %u", cap, max_val + 1);
+    const float *table = nullptr;
+    switch (ptf) {
+    case LUMACU_PTF_PQ:
+        for (unsigned i = 0; i <= max_val; i++)
+            lut_out[i] = host_pq_decode((float)i / max_val, max_lum);
+        return LUMACU_OK;
+    case LUMACU_PTF_LOG: {
+        for (unsigned i = 0; i <= max_val; i++) {
+            float v = (float)i / max_val;
+            lut_out[i] = powf(10.0f, v * (log10f(max_lum) - log10f(min_lum)) + log10f(min_lum));
+        }
+        return LUMACU_OK;
+    }
+    case LUMACU_PTF_LINEAR:
+        for (unsigned i = 0; i <= max_val; i++)
+            lut_out[i] = max_lum * ((float)i / max_val);
+        return LUMACU_OK;
+#ifdef LUMA_HAVE_PTF_TABLES
+    case LUMACU_PTF_JND_HDRVDP:
+        table = bitdepth == 10 ? k_ptf_vdp_10 : bitdepth == 11 ? k_ptf_vdp_11 : k_ptf_vdp_12;
+        break;
+    case LUMACU_PTF_PSI:
+        table = bitdepth == 10 ? k_ptf_psi_10 : bitdepth == 11 ? k_ptf_psi_11 : k_ptf_psi_12;
+        break;
+#else
+    case LUMACU_PTF_JND_HDRVDP:
+    case LUMACU_PTF_PSI:
+        (void)table;
+        return fail(nullptr, LUMACU_ERR_UNSUPPORTED,
+                    "lumacu_build_lut: library was built without the reference's ptfs/ tables");
+#endif
+    default:
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_build_lut: unknown ptf %d", ptf);
+    }
+#ifdef LUMA_HAVE_PTF_TABLES
+    /* any depth other than 10/11 reads the 12-bit table (reference quirk, :131-143); the
+     * reference would read past its end for depths above 12 -- refuse instead */
+    if (max_val + 1 > 4096u)
+        return fail(nullptr, LUMACU_ERR_UNSUPPORTED, "lumacu_build_lut: table PTFs hold at most 4096 entries");
+    for (unsigned i = 0; i <= max_val; i++)
+        lut_out[i] = table[i];
+    return LUMACU_OK;
+#endif
+}
+
+/* Thresholds of the reference's nearest-code decision.  Returns 1 and fills
+ * thr_keys[0 .. lut_len-2] (ordered keys, strictly increasing) when the LUT is
+ * finite and strictly increasing; returns 0 otherwise (literal search needed). */
+extern "C" int lumacu_derive_thresholds(const float *lut, uint32_t lut_len, uint32_t *thr_keys)
+{
+    if (!lut || lut_len < 2 || !thr_keys)
+        return 0;
+    for (uint32_t i = 0; i < lut_len; i++)
+        if (!isfinite(lut[i]) || (i && !(lut[i - 1] < lut[i])))
+            return 0;
+    for (uint32_t k = 1; k < lut_len; k++) {
+        const float ml = lut[k - 1], mr = lut[k];
+        /* predicate picks_upper is false at ml, true at mr, monotone in between */
+        uint32_t lo = key_of(ml), hi = key_of(mr);
+        while (hi - lo > 1) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            if (picks_upper(float_of_key(mid), ml, mr))
+                hi = mid;
+            else
+                lo = mid;
+        }
+        thr_keys[k - 1] = hi;
+    }
+    return 1;
+}
+
+/* Chooses the bucket table: the finest key shift whose table has at most
+ * kMaxBuckets entries; walk = the largest number of thresholds in one bucket. */
+extern "C" int lumacu_plan_buckets(const uint32_t *thr_keys, uint32_t n_thr, uint32_t *shift, uint32_t *base,
+                                   uint32_t *n_buckets, uint32_t *walk)
+{
+    if (!thr_keys || !n_thr)
+        return 0;
+    for (uint32_t s = 8; s <= 31; s++) {
+        const uint32_t b0 = thr_keys[0] >> s, b1 = thr_keys[n_thr - 1] >> s;
+        const uint32_t nb = b1 - b0 + 1;
+        if (nb > kMaxBuckets)
+            continue;
+        uint32_t w = 0, run = 0, cur = b0;
+        for (uint32_t i = 0; i < n_thr; i++) {
+            uint32_t b = thr_keys[i] >> s;
+            if (b != cur) {
+                cur = b;
+                run = 0;
+            }
+            run++;
+            w = std::max(w, run);
+        }
+        *shift = s;
+        *base = b0;
+        *n_buckets = nb;
+        *walk = w;
+        return 1;
+    }
+    return 0;
+}
+
+/* ================================ context ============================================ */
+
+extern "C" int lumacu_create(int device, lumacu_ctx **out)
+{
+    if (!out)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LUMACU_ERR_NO_DEVICE, "lumacu_create: no CUDA device (%s)",
+                    e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_create: device %d out of range [0,%d)", device, n);
+    lumacu_ctx *ctx = new (std::nothrow) lumacu_ctx();
+    if (!ctx)
+        return fail(nullptr, LUMACU_ERR_OUT_OF_MEMORY, "lumacu_create: host allocation failed");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, LUMACU_ERR_CUDA, "lumacu_create: %s", cudaGetErrorString(e));
+    }
+    if (prop.major != 10) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, LUMACU_ERR_UNSUPPORTED, "lumacu_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_destroy(lumacu_ctx *ctx)
+{
+    if (!ctx)
+        return LUMACU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
+                            &ctx->d_aux})
+        if (b->p)
+            cudaFree(b->p);
+    if (ctx->h_pin)
+        cudaFreeHost(ctx->h_pin);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return LUMACU_OK;
+}
+
+extern "C" const char *lumacu_last_error(const lumacu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int lumacu_device(const lumacu_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uint64_t lumacu_launch_count(const lumacu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lumacu_synchronize(lumacu_ctx *ctx)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LUMACU_OK;
+}
+
+extern "C" void *lumacu_stream(lumacu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int lumacu_host_alloc(size_t bytes, void **out)
+{
+    if (!out)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        cudaGetLastError();
+        return fail(nullptr, LUMACU_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+    return LUMACU_OK;
+}
+
+/* ================================ quantizer ========================================== */
+
+extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t lut_len, uint32_t max_val_color,
+                                    int color_space, float max_lum)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!lut || lut_len < 1 || lut_len > 65536u)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: lut_len %u not in [1,65536]", lut_len);
+    if (color_space < 0 || color_space > 3)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: unknown colour space %d", color_space);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+
+    const uint32_t max_val = lut_len - 1;
+    std::vector<uint32_t> thr(max_val ? max_val : 1);
+    std::vector<uint16_t> bucket;
+    uint32_t shift = 0, base = 0, nb = 0, walk = 0;
+    int mode = SEARCH_LITERAL;
+    if (max_val >= 1 && lumacu_derive_thresholds(lut, lut_len, thr.data())) {
+        mode = SEARCH_BINARY;
+        if (lumacu_plan_buckets(thr.data(), max_val, &shift, &base, &nb, &walk) && walk <= kMaxWalk) {
+            mode = SEARCH_BUCKET;
+            bucket.assign(nb + (nb & 1u) + 2u, 0);
+            /* head[b] = number of thresholds in lower buckets */
+            uint32_t j = 0;
+            for (uint32_t b = 0; b < nb; b++) {
+                while (j < max_val && (thr[j] >> shift) - base < b)
+                    j++;
+                bucket[b] = (uint16_t)j;
+            }
+        }
+    }
+    const uint32_t pad = std::max(walk, 2u);
+    const uint32_t thr_count = (mode == SEARCH_LITERAL) ? 0u : max_val + pad;
+    if (mode != SEARCH_LITERAL)
+        thr.resize(thr_count, 0xFFFFFFFFu);
+
+    /* one device allocation: lut | thr | bucket */
+    const size_t off_thr = ((size_t)lut_len * 4 + 15) & ~(size_t)15;
+    const size_t off_bucket = (off_thr + (size_t)thr_count * 4 + 15) & ~(size_t)15;
+    const size_t total = off_bucket + bucket.size() * 2 + 16;
+    int rc = reserve(ctx, ctx->d_tables, total);
+    if (rc)
+        return rc;
+    /* previous launches may still read the old tables */
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned char *d = (unsigned char *)ctx->d_tables.p;
+    CU_TRY(ctx, cudaMemcpy(d, lut, (size_t)lut_len * 4, cudaMemcpyHostToDevice));
+    if (thr_count)
+        CU_TRY(ctx, cudaMemcpy(d + off_thr, thr.data(), (size_t)thr_count * 4, cudaMemcpyHostToDevice));
+    if (!bucket.empty())
+        CU_TRY(ctx, cudaMemcpy(d + off_bucket, bucket.data(), bucket.size() * 2, cudaMemcpyHostToDevice));
+
+    QuantDev q{};
+    q.lut = (const float *)d;
+    q.thr = (const uint32_t *)(d + off_thr);
+    q.bucket = (const uint16_t *)(d + off_bucket);
+    q.max_val = max_val;
+    q.max_val_color = max_val_color;
+    q.max_val_f = (float)max_val;
+    q.max_val_color_f = (float)max_val_color;
+    q.l_max = max_lum;
+    q.search_mode = mode;
+    q.shift = shift;
+    q.base = base;
+    q.nbm1 = nb ? nb - 1 : 0;
+    q.walk = walk;
+    q.thr_count = thr_count;
+    size_t smem_enc = 0;
+    if (mode != SEARCH_LITERAL) {
+        smem_enc = (size_t)thr_count * 4 + (mode == SEARCH_BUCKET ? ((size_t)(nb + 2) / 2) * 4 : 0);
+        if (smem_enc > kMaxSmemTables)
+            smem_enc = 0;
+    }
+    q.smem_tables = smem_enc ? 1u : 0u;
+    size_t smem_dec = (size_t)lut_len * 4;
+    if (smem_dec > kMaxSmemLut)
+        smem_dec = 0;
+    q.smem_lut = smem_dec ? 1u : 0u;
+
+    ctx->q = q;
+    ctx->smem_enc = smem_enc;
+    ctx->smem_dec = smem_dec;
+    ctx->color_space = color_space;
+    ctx->h_lut.assign(lut, lut + lut_len);
+    ctx->configured = true;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift, uint32_t *walk)
+{
+    if (!ctx || !ctx->configured)
+        return LUMACU_ERR_NOT_CONFIGURED;
+    if (mode)
+        *mode = ctx->q.search_mode;
+    if (n_buckets)
+        *n_buckets = ctx->q.search_mode == SEARCH_BUCKET ? ctx->q.nbm1 + 1 : 0;
+    if (shift)
+        *shift = ctx->q.shift;
+    if (walk)
+        *walk = ctx->q.walk;
+    return LUMACU_OK;
+}
+
+/* ================================ launches ============================================ */
+namespace {
+
+typedef void (*enc_fn)(const EncArgs);
+typedef void (*dec_fn)(const DecArgs);
+
+template <int CS>
+enc_fn pick_enc_cs(bool sub, int bytes, bool vec)
+{
+    if (sub) {
+        if (bytes == 2)
+            return vec ? encode_kernel<CS, true, 2, true> : encode_kernel<CS, true, 2, false>;
+        return vec ? encode_kernel<CS, true, 1, true> : encode_kernel<CS, true, 1, false>;
+    }
+    if (bytes == 2)
+        return vec ? encode_kernel<CS, false, 2, true> : encode_kernel<CS, false, 2, false>;
+    return vec ? encode_kernel<CS, false, 1, true> : encode_kernel<CS, false, 1, false>;
+}
+enc_fn pick_enc(int cs, bool sub, int bytes, bool vec)
+{
+    switch (cs) {
+    case CS_LUV: return pick_enc_cs<CS_LUV>(sub, bytes, vec);
+    case CS_RGB: return pick_enc_cs<CS_RGB>(sub, bytes, vec);
+    case CS_YCBCR: return pick_enc_cs<CS_YCBCR>(sub, bytes, vec);
+    default: return pick_enc_cs<CS_XYZ>(sub, bytes, vec);
+    }
+}
+template <int CS>
+dec_fn pick_dec_cs(bool sub, int bytes, bool vec)
+{
+    if (sub) {
+        if (bytes == 2)
+            return vec ? decode_kernel<CS, true, 2, true> : decode_kernel<CS, true, 2, false>;
+        return vec ? decode_kernel<CS, true, 1, true> : decode_kernel<CS, true, 1, false>;
+    }
+    if (bytes == 2)
+        return vec ? decode_kernel<CS, false, 2, true> : decode_kernel<CS, false, 2, false>;
+    return vec ? decode_kernel<CS, false, 1, true> : decode_kernel<CS, false, 1, false>;
+}
+dec_fn pick_dec(int cs, bool sub, int bytes, bool vec)
+{
+    switch (cs) {
+    case CS_LUV: return pick_dec_cs<CS_LUV>(sub, bytes, vec);
+    case CS_RGB: return pick_dec_cs<CS_RGB>(sub, bytes, vec);
+    case CS_YCBCR: return pick_dec_cs<CS_YCBCR>(sub, bytes, vec);
+    default: return pick_dec_cs<CS_XYZ>(sub, bytes, vec);
+    }
+}
+
+inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+/* persistent grid: resident blocks on the whole chip, capped by the work */
+int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint32_t n_frames, uint32_t *gx)
+{
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem));
+    if (per_sm < 1)
+        return fail(ctx, LUMACU_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    uint32_t resident = (uint32_t)per_sm * (uint32_t)ctx->sm_count;
+    uint32_t need = (ntiles + kThreads - 1) / kThreads;
+    uint32_t g = resident;
+    if (n_frames > 1) {
+        /* several frames per launch: spread the resident slots over the frames, but keep
+         * at least ~8 tiles per thread so that table staging stays amortised */
+        uint32_t per_frame = (resident + n_frames - 1) / n_frames;
+        uint32_t coarse = (need + 7) / 8;
+        g = std::max(per_frame, std::min(coarse, resident));
+    }
+    *gx = std::max(1u, std::min(g, need));
+    return LUMACU_OK;
+}
+
+int check_profile(lumacu_ctx *ctx, int profile, uint32_t w, uint32_t h, bool encode)
+{
+    if (profile < 0 || profile > 3)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "profile %d not in [0,3]", profile);
+    if (w == 0 || h == 0)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "frame size %ux%u is empty", w, h);
+    const bool sub = (profile == 0 || profile == 2);
+    /* the reference encoder refuses odd sizes (src/luma_encoder.cpp:118-119); its 4:2:0
+     * decoder loop indexes as if the width were even (src/luma_decoder.cpp:229-234) */
+    if ((encode || sub) && ((w | h) & 1u))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "frame size %ux%u must be even", w, h);
+    if ((uint64_t)w * h > 0x7fffffffull)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "frame size %ux%u too large", w, h);
+    return LUMACU_OK;
+}
+
+} // namespace
+
+extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, uint32_t w, uint32_t h,
+                                 int profile, float pre_scaling, uint8_t *const d_planes[3], const int32_t strides[3],
+                                 uint32_t n_frames, size_t rgb_frame_stride, const size_t plane_frame_stride[3],
+                                 lumacu_frame_stats *d_stats, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_encode_dev: lumacu_set_quantizer has not been called");
+    if (!d_rgb || !d_planes || !strides || !d_planes[0] || !d_planes[1] || !d_planes[2])
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode_dev: NULL pointer argument");
+    int rc = check_profile(ctx, profile, w, h, true);
+    if (rc)
+        return rc;
+    if (n_frames == 0)
+        return LUMACU_OK;
+    if (n_frames > 65535u)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode_dev: at most 65535 frames per launch");
+    const bool sub = (profile == 0 || profile == 2);
+    const int bytes = profile > 1 ? 2 : 1;
+    const uint32_t cw = sub ? (w + 1) >> 1 : w, chh = sub ? (h + 1) >> 1 : h;
+    if (strides[0] < (int32_t)(w * bytes) || strides[1] < (int32_t)(cw * bytes) || strides[2] < (int32_t)(cw * bytes))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode_dev: stride smaller than a row");
+    if (n_frames > 1 && !plane_frame_stride)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode_dev: plane_frame_stride required for n_frames > 1");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+
+    EncArgs a{};
+    a.q = ctx->q;
+    a.rgb = d_rgb;
+    a.rgb_out = d_rgb_out;
+    a.rgb_plane_stride = (size_t)w * h;
+    a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
+    a.out_plane_stride = a.rgb_plane_stride;
+    a.out_frame_stride = a.rgb_frame_stride;
+    a.w = w;
+    a.h = h;
+    a.sc = pre_scaling;
+    a.prescale = (pre_scaling != 1.0f) ? 1 : 0;
+    bool vec = (w % 4 == 0) && aligned(d_rgb, 16) && (a.rgb_frame_stride % 4 == 0) && (a.rgb_plane_stride % 4 == 0) &&
+               (!d_rgb_out || aligned(d_rgb_out, 16));
+    for (int p = 0; p < 3; p++) {
+        a.plane[p] = d_planes[p];
+        a.stride[p] = strides[p];
+        a.plane_frame_stride[p] = plane_frame_stride ? plane_frame_stride[p] : (size_t)strides[p] * (p ? chh : h);
+        const size_t al = (size_t)((p && sub) ? 2 : 4) * bytes; /* bytes stored per thread and row */
+        vec = vec && aligned(d_planes[p], al) && (strides[p] % al == 0) && (a.plane_frame_stride[p] % al == 0);
+    }
+    enc_fn fn = pick_enc(ctx->color_space, sub, bytes, vec);
+    const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
+    uint32_t gx = 1;
+    rc = grid_for(ctx, (const void *)fn, ctx->smem_enc, ntiles, n_frames, &gx);
+    if (rc)
+        return rc;
+    if (d_stats) {
+        rc = reserve(ctx, ctx->d_partial, (size_t)n_frames * gx * sizeof(StatsPartial));
+        if (rc)
+            return rc;
+        if ((size_t)n_frames * 4 > ctx->d_counter.cap) {
+            rc = reserve(ctx, ctx->d_counter, std::max<size_t>((size_t)n_frames * 4, 4096));
+            if (rc)
+                return rc;
+            CU_TRY(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, ctx->d_counter.cap, st));
+        }
+        a.partial = (StatsPartial *)ctx->d_partial.p;
+        a.counter = (uint32_t *)ctx->d_counter.p;
+        a.stats = (FrameStatsDev *)d_stats;
+    }
+    fn<<<dim3(gx, n_frames), kThreads, ctx->smem_enc, st>>>(a);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
+                                 uint32_t h, int profile, float pre_scaling, float *d_rgb, uint32_t n_frames,
+                                 size_t rgb_frame_stride, const size_t plane_frame_stride[3], void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_decode_dev: lumacu_set_quantizer has not been called");
+    if (!d_rgb || !d_planes || !strides || !d_planes[0] || !d_planes[1] || !d_planes[2])
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_dev: NULL pointer argument");
+    int rc = check_profile(ctx, profile, w, h, false);
+    if (rc)
+        return rc;
+    if (n_frames == 0)
+        return LUMACU_OK;
+    if (n_frames > 65535u)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_dev: at most 65535 frames per launch");
+    const bool sub = (profile == 0 || profile == 2);
+    const int bytes = profile > 1 ? 2 : 1;
+    const uint32_t cw = sub ? (w + 1) >> 1 : w, chh = sub ? (h + 1) >> 1 : h;
+    if (strides[0] < (int32_t)(w * bytes) || strides[1] < (int32_t)(cw * bytes) || strides[2] < (int32_t)(cw * bytes))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_dev: stride smaller than a row");
+    if (n_frames > 1 && !plane_frame_stride)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_dev: plane_frame_stride required for n_frames > 1");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+
+    DecArgs a{};
+    a.q = ctx->q;
+    a.rgb = d_rgb;
+    a.rgb_plane_stride = (size_t)w * h;
+    a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
+    a.w = w;
+    a.h = h;
+    a.sc = pre_scaling;
+    a.prescale = (pre_scaling != 1.0f) ? 1 : 0;
+    bool vec = (w % 4 == 0) && aligned(d_rgb, 16) && (a.rgb_frame_stride % 4 == 0) && (a.rgb_plane_stride % 4 == 0);
+    for (int p = 0; p < 3; p++) {
+        a.plane[p] = d_planes[p];
+        a.stride[p] = strides[p];
+        a.plane_frame_stride[p] = plane_frame_stride ? plane_frame_stride[p] : (size_t)strides[p] * (p ? chh : h);
+        const size_t al = (size_t)((p && sub) ? 2 : 4) * bytes;
+        vec = vec && aligned(d_planes[p], al) && (strides[p] % al == 0) && (a.plane_frame_stride[p] % al == 0);
+    }
+    dec_fn fn = pick_dec(ctx->color_space, sub, bytes, vec);
+    const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
+    uint32_t gx = 1;
+    rc = grid_for(ctx, (const void *)fn, ctx->smem_dec, ntiles, n_frames, &gx);
+    if (rc)
+        return rc;
+    fn<<<dim3(gx, n_frames), kThreads, ctx->smem_dec, st>>>(a);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame, uint32_t w, uint32_t h, int to_cs, float sc,
+                                                void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_transform_color_space_dev: quantizer not set");
+    if (!d_frame)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_transform_color_space_dev: NULL frame");
+    const size_t n = (size_t)w * h;
+    if (!n)
+        return LUMACU_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 16);
+    float *c0 = d_frame, *c1 = d_frame + n, *c2 = d_frame + 2 * n;
+    const float L = ctx->q.l_max;
+#define LAUNCH_T(CSV)                                                                        \
+    if (to_cs)                                                                               \
+        transform_kernel<CSV, true><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, L);      \
+    else                                                                                     \
+        transform_kernel<CSV, false><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, L);
+    switch (ctx->color_space) {
+    case CS_LUV: LAUNCH_T(CS_LUV) break;
+    case CS_RGB: LAUNCH_T(CS_RGB) break;
+    case CS_YCBCR: LAUNCH_T(CS_YCBCR) break;
+    default: LAUNCH_T(CS_XYZ) break;
+    }
+#undef LAUNCH_T
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+static bool channel_uses_lut(const lumacu_ctx *ctx, unsigned ch)
+{
+    return ch == 0 || ctx->color_space == CS_RGB || ctx->color_space == CS_XYZ;
+}
+
+extern "C" int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_quantize_dev: quantizer not set");
+    if (!n)
+        return LUMACU_OK;
+    if (!d_in || !d_out)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_quantize_dev: NULL pointer");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const void *fn = (const void *)quantize_kernel;
+    if (ctx->smem_enc > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_enc));
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 4);
+    quantize_kernel<<<blocks, kThreads, ctx->smem_enc, st>>>(ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_dequantize_dev: quantizer not set");
+    if (!n)
+        return LUMACU_OK;
+    if (!d_in || !d_out)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_dequantize_dev: NULL pointer");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    dequantize_kernel<<<blocks, kThreads, 0, st>>>(ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+/* ================================ host-pointer entry points ========================== */
+namespace {
+
+void plane_geometry(uint32_t w, uint32_t h, int profile, uint32_t pw[3], uint32_t ph[3])
+{
+    const bool sub = (profile == 0 || profile == 2);
+    pw[0] = w;
+    ph[0] = h;
+    pw[1] = pw[2] = sub ? (w + 1) >> 1 : w;
+    ph[1] = ph[2] = sub ? (h + 1) >> 1 : h;
+}
+
+/* device-side plane layout used by the host entry points: 256-byte aligned pitches */
+void device_plane_layout(uint32_t w, uint32_t h, int profile, int32_t dstride[3], size_t off[3], size_t *total)
+{
+    uint32_t pw[3], ph[3];
+    plane_geometry(w, h, profile, pw, ph);
+    const int bytes = profile > 1 ? 2 : 1;
+    size_t o = 0;
+    for (int p = 0; p < 3; p++) {
+        dstride[p] = (int32_t)(((size_t)pw[p] * bytes + 255) & ~(size_t)255);
+        off[p] = o;
+        o += (size_t)dstride[p] * ph[p];
+    }
+    *total = o;
+}
+
+} // namespace
+
+extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
+                             uint8_t *const planes[3], const int32_t strides[3], int write_back,
+                             lumacu_frame_stats *stats)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_encode: lumacu_set_quantizer has not been called");
+    if (!rgb || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode: NULL pointer argument");
+    int rc = check_profile(ctx, profile, w, h, true);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    uint32_t pw[3], ph[3];
+    plane_geometry(w, h, profile, pw, ph);
+    const int bytes = profile > 1 ? 2 : 1;
+    for (int p = 0; p < 3; p++)
+        if (strides[p] < (int32_t)(pw[p] * bytes))
+            return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode: stride[%d] smaller than a row", p);
+    int32_t dstride[3];
+    size_t off[3], ptotal;
+    device_plane_layout(w, h, profile, dstride, off, &ptotal);
+    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) ||
+        (rc = reserve(ctx, ctx->d_stats, sizeof(lumacu_frame_stats))))
+        return rc;
+    float *d_rgb = (float *)ctx->d_rgb.p;
+    uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
+                      (uint8_t *)ctx->d_planes.p + off[2]};
+    CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, npx * 12, cudaMemcpyHostToDevice, ctx->stream));
+    rc = lumacu_encode_dev(ctx, d_rgb, write_back ? d_rgb : nullptr, w, h, profile, pre_scaling, dp, dstride, 1, 0, nullptr,
+                           stats ? (lumacu_frame_stats *)ctx->d_stats.p : nullptr, ctx->stream);
+    if (rc)
+        return rc;
+    for (int p = 0; p < 3; p++)
+        CU_TRY(ctx, cudaMemcpy2DAsync(planes[p], (size_t)strides[p], dp[p], (size_t)dstride[p], (size_t)pw[p] * bytes, ph[p],
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    if (write_back)
+        CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats)
+        CU_TRY(ctx, cudaMemcpyAsync(stats, ctx->d_stats.p, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                             uint32_t h, int profile, float pre_scaling, float *rgb)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_decode: lumacu_set_quantizer has not been called");
+    if (!rgb || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode: NULL pointer argument");
+    int rc = check_profile(ctx, profile, w, h, false);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    uint32_t pw[3], ph[3];
+    plane_geometry(w, h, profile, pw, ph);
+    const int bytes = profile > 1 ? 2 : 1;
+    for (int p = 0; p < 3; p++)
+        if (strides[p] < (int32_t)(pw[p] * bytes))
+            return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode: stride[%d] smaller than a row", p);
+    int32_t dstride[3];
+    size_t off[3], ptotal;
+    device_plane_layout(w, h, profile, dstride, off, &ptotal);
+    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)))
+        return rc;
+    float *d_rgb = (float *)ctx->d_rgb.p;
+    const uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
+                            (uint8_t *)ctx->d_planes.p + off[2]};
+    for (int p = 0; p < 3; p++)
+        CU_TRY(ctx, cudaMemcpy2DAsync((void *)dp[p], (size_t)dstride[p], planes[p], (size_t)strides[p], (size_t)pw[p] * bytes,
+                                      ph[p], cudaMemcpyHostToDevice, ctx->stream));
+    rc = lumacu_decode_dev(ctx, dp, dstride, w, h, profile, pre_scaling, d_rgb, 1, 0, nullptr, ctx->stream);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs, float sc)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_transform_color_space: quantizer not set");
+    if (!frame)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_transform_color_space: NULL frame");
+    const size_t bytes = (size_t)w * h * 12;
+    if (!bytes)
+        return LUMACU_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->d_rgb, bytes);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb.p, frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = lumacu_transform_color_space_dev(ctx, (float *)ctx->d_rgb.p, w, h, to_cs, sc, ctx->stream);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(frame, ctx->d_rgb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LUMACU_OK;
+}
+
+static int elementwise_host(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch, bool quant)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "quantizer not set");
+    if (!n)
+        return LUMACU_OK;
+    if (!in || !out)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "NULL pointer");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->d_aux, n * 8);
+    if (rc)
+        return rc;
+    float *d_in = (float *)ctx->d_aux.p, *d_out = d_in + n;
+    CU_TRY(ctx, cudaMemcpyAsync(d_in, in, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = quant ? lumacu_quantize_dev(ctx, d_in, d_out, n, ch, ctx->stream)
+               : lumacu_dequantize_dev(ctx, d_in, d_out, n, ch, ctx->stream);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_quantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch)
+{
+    return elementwise_host(ctx, in, out, n, ch, true);
+}
+
+extern "C" int lumacu_dequantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch)
+{
+    return elementwise_host(ctx, in, out, n, ch, false);
+}

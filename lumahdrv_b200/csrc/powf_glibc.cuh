@@ -1,0 +1,116 @@
+/*
+ * powf_glibc.cuh -- device restatement of the host libm's powf.
+ *
+ * The reference evaluates PQ per pixel for CS_YCBCR through libm powf
+ * (/root/reference/src/luma_quantizer.cpp:493-499).  The reference neither
+ * vendors nor pins a libm: results are "whatever glibc returns".  glibc's powf
+ * (2.28 ... 2.39, sysdeps/ieee754/flt-32/e_powf.c, derived from ARM's
+ * optimized-routines) is < 1 ulp but not correctly rounded, so neither CUDA's
+ * powf nor a double-precision pow reproduces its bits.  This header restates
+ * the published algorithm: log2(x) from a 16-entry {1/c, log2 c} table plus a
+ * degree-5 polynomial, times y, then exp2 through a 32-entry 2^(i/32) table
+ * and a cubic, all in IEEE double with SEPARATE multiplies and adds (no FMA),
+ * which is what the host executes.  tools/powf_check.c replays the same
+ * sequence on the CPU against the host powf (0 mismatches in 8e8 PQ-domain
+ * calls on glibc 2.39-0ubuntu8.5).
+ *
+ * Restricted to what the PQ call sites need: y is a finite, positive,
+ * non-integer constant (0.1593f, 78.8438f and their fp32 reciprocals); x is
+ * any float.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lumacu {
+
+/* __powf_log2_data (POWF_LOG2_TABLE_BITS = 4, POWF_SCALE_BITS = 0) */
+__device__ const double2 k_powf_log2_tab[16] = {
+    {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
+    {0x1.49539f0f010bp+0, -0x1.7418b0a1fb77bp-2},  {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
+    {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8eap+0, -0x1.97c1d1b3b7afp-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3}, {0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4},
+    {0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4},  {0x1.ca4b31f026aap-1, 0x1.476a9543891bap-3},
+    {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},
+    {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},  {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}};
+
+/* __exp2f_data.tab (EXP2F_TABLE_BITS = 5): bits of 2^(i/32) with the exponent
+ * contribution i << 47 subtracted */
+__device__ const unsigned long long k_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+__device__ __forceinline__ float powf_glibc(float x, float y)
+{
+    uint32_t ix = __float_as_uint(x);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        /* x < 0x1p-126, or inf, or nan (e_powf.c "zeroinfnan (ix)" and below) */
+        if (2u * ix - 1u >= 2u * 0x7f800000u - 1u)
+            return __fmul_rn(x, x); /* +-0 -> +0, +-inf -> +inf, nan -> nan (y > 0, not an odd integer) */
+        if (ix & 0x80000000u)
+            return __int_as_float(0x7fffffff); /* finite x < 0, non-integer y: invalid */
+        /* normalise a subnormal x so that the exponent goes negative */
+        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));
+        ix &= 0x7fffffffu;
+        ix -= 23u << 23;
+    }
+
+    /* log2_inline: x = 2^k z, z in [OFF, 2 OFF), c near the centre of z's subinterval */
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> (23 - 4)) & 15u);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int k = (int32_t)top >> 23;
+    const double2 tc = k_powf_log2_tab[i];
+    const double z = (double)__uint_as_float(iz);
+
+    const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2,
+                 A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
+    const double r = __dadd_rn(__dmul_rn(z, tc.x), -1.0);
+    const double y0 = __dadd_rn(tc.y, (double)k);
+    const double r2 = __dmul_rn(r, r);
+    double yy = __dadd_rn(__dmul_rn(A0, r), A1);
+    const double p = __dadd_rn(__dmul_rn(A2, r), A3);
+    const double r4 = __dmul_rn(r2, r2);
+    double q = __dadd_rn(__dmul_rn(A4, r), y0);
+    q = __dadd_rn(__dmul_rn(p, r2), q);
+    yy = __dadd_rn(__dmul_rn(yy, r4), q);
+
+    const double ylogx = __dmul_rn((double)y, yy);
+    const uint32_t top16 = (uint32_t)(((unsigned long long)__double_as_longlong(ylogx) >> 47) & 0xffffu);
+    if (top16 >= (uint32_t)((unsigned long long)0x405f800000000000ull >> 47)) { /* |y log2 x| >= 126 */
+        if (ylogx > 0x1.fffffffd1d571p+6)
+            return __int_as_float(0x7f800000); /* overflow */
+        if (ylogx <= -150.0)
+            return 0.0f; /* underflow */
+        if (ylogx < -149.0)
+            return __int_as_float(0x00000001); /* __math_may_uflowf: 0x1.4p-75f squared */
+    }
+
+    /* exp2_inline: x = k/N + r, |r| <= 1/(2N), N = 32 */
+    const double SHIFT = 0x1.8p+47; /* 0x1.8p52 / N */
+    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    double kd = __dadd_rn(ylogx, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -SHIFT);
+    const double rr = __dadd_rn(ylogx, -kd);
+    unsigned long long t = k_exp2f_tab[ki & 31u];
+    t += ki << (52 - 5);
+    const double s = __longlong_as_double((long long)t);
+    const double zz = __dadd_rn(__dmul_rn(C0, rr), C1);
+    const double rr2 = __dmul_rn(rr, rr);
+    double o = __dadd_rn(__dmul_rn(C2, rr), 1.0);
+    o = __dadd_rn(__dmul_rn(zz, rr2), o);
+    o = __dmul_rn(o, s);
+    return __double2float_rn(o);
+}
+
+} // namespace lumacu

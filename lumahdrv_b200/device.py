@@ -1,0 +1,113 @@
+"""Device-resident batch API: frames and planes stay in HBM as torch tensors.
+
+torch is plumbing only (allocation, streams, ``torch.distributed``); every pixel
+is produced by the kernels behind ``lumacu_encode_dev`` / ``lumacu_decode_dev``.
+
+Frame batches are ``float32 [n, 3, h, w]`` (n LumaFrames back to back); plane
+batches are three ``uint8 [n, rows, stride]`` tensors (n vpx-style pitched planes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import LumaException, check
+from .luma import Context, LumaQuantizer, plane_dims, vpx_strides
+
+STATS_DTYPE = np.dtype([("sum", "<f8"), ("max", "<f4"), ("min", "<f4")])
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceTransform:
+    """Encode/decode frame batches that already live on one GPU."""
+
+    def __init__(self, device: int | torch.device = 0, ptf="PQ", ptfBitDepth: int = 11, colorSpace="LUV",
+                 colorBitDepth: int = 8, maxLum: float = 1e4, minLum: float = 0.005, profile: int = 2,
+                 preScaling: float = 1.0, lut: np.ndarray | None = None):
+        if not torch.cuda.is_available():
+            raise LumaException("DeviceTransform needs a CUDA device (there is no CPU fallback)", 6)
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.quant = LumaQuantizer(context=Context(self.index))
+        self.quant.setQuantizer(ptf, ptfBitDepth, colorSpace, colorBitDepth, maxLum, minLum)
+        if lut is not None:  # e.g. a LUT received from rank 0
+            self.quant.setMapping(lut)
+            self.quant._upload()
+        self.profile = int(profile)
+        self.preScaling = float(preScaling)
+        self._lib = self.quant._lib
+
+    # ------------------------------------------------------------------ geometry
+    def alloc_planes(self, n: int, w: int, h: int, strides=None):
+        strides = strides or vpx_strides(w, self.profile)
+        return [torch.zeros((n, ph, st), dtype=torch.uint8, device=self.device)
+                for (pw, ph), st in zip(plane_dims(w, h, self.profile), strides)]
+
+    def alloc_stats(self, n: int) -> torch.Tensor:
+        return torch.zeros((n, STATS_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+
+    @staticmethod
+    def stats_to_numpy(stats: torch.Tensor) -> np.ndarray:
+        return stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
+
+    @staticmethod
+    def _plane_args(planes):
+        n = planes[0].shape[0]
+        for p in planes:
+            if p.dtype != torch.uint8 or p.dim() != 3 or not p.is_contiguous() or p.shape[0] != n:
+                raise LumaException("planes must be contiguous uint8 [n, rows, stride] tensors", 1)
+        ptrs = (C.c_void_p * 3)(*[p.data_ptr() for p in planes])
+        strides = (C.c_int32 * 3)(*[p.shape[2] for p in planes])
+        fstr = (C.c_size_t * 3)(*[p.shape[1] * p.shape[2] for p in planes])
+        return n, ptrs, strides, fstr
+
+    # ------------------------------------------------------------------ transform
+    def encode(self, rgb: torch.Tensor, planes=None, stats: torch.Tensor | None = None,
+               write_back: torch.Tensor | None = None):
+        """n x LumaEncoder::encode (minus run()) in one launch.  Asynchronous on the current stream."""
+        if rgb.dtype != torch.float32 or rgb.dim() != 4 or rgb.shape[1] != 3 or not rgb.is_contiguous() or not rgb.is_cuda:
+            raise LumaException("rgb must be a contiguous CUDA float32 [n, 3, h, w] tensor", 1)
+        n, _, h, w = rgb.shape
+        planes = planes if planes is not None else self.alloc_planes(n, w, h)
+        pn, ptrs, strides, fstr = self._plane_args(planes)
+        if pn != n:
+            raise LumaException("frame and plane batch sizes differ", 1)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_encode_dev(hnd, rgb.data_ptr(), write_back.data_ptr() if write_back is not None else None,
+                                          w, h, self.profile, self.preScaling, ptrs, strides, n, 3 * h * w, fstr,
+                                          stats.data_ptr() if stats is not None else None, _stream_ptr(self.device)),
+              hnd, "lumacu_encode_dev")
+        return planes
+
+    def decode(self, planes, w: int, h: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """n x LumaDecoder::decode (minus run()) in one launch.  Asynchronous on the current stream."""
+        n, ptrs, strides, fstr = self._plane_args(planes)
+        if out is None:
+            out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_decode_dev(hnd, ptrs, strides, w, h, self.profile, self.preScaling, out.data_ptr(), n,
+                                          3 * h * w, fstr, _stream_ptr(self.device)), hnd, "lumacu_decode_dev")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return self.quant.ctx.launch_count
+
+
+def broadcast_quantizer_lut(lut: np.ndarray | None, n_entries: int, device: torch.device, src: int = 0) -> np.ndarray:
+    """Share rank ``src``'s host-built LUT with every rank (NCCL broadcast of <= 256 KB).
+
+    The LUT is built with the host libm on one rank so that all shards quantise with the
+    same table even if host libms differ; no pixel data ever crosses GPUs."""
+    import torch.distributed as dist
+
+    t = torch.empty(n_entries, dtype=torch.float32, device=device)
+    if dist.get_rank() == src:
+        t.copy_(torch.from_numpy(np.ascontiguousarray(lut, dtype=np.float32)))
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()

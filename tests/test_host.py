@@ -1,0 +1,119 @@
+"""CPU: host logic of the product library (no compute calls, no GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_abi_exports_every_declared_symbol(lumalib):
+    header = (ROOT / "include" / "lumacu.h").read_text()
+    declared = set(re.findall(r"\b(lumacu_[a-z0-9_]+)\s*\(", header))
+    declared -= {"lumacu_ctx", "lumacu_status"}  # "a lumacu_status (0 = OK)" in the prose
+    from lumahdrv_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = lumalib.lib()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.lumacu_version() == 100
+    assert handle.lumacu_status_name(6) == b"LUMACU_ERR_NO_DEVICE"
+
+
+def test_no_cpu_fallback_without_device(lumalib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lumalib.LumaException, match="NO_DEVICE"):
+        lumalib.Context(0)
+    with pytest.raises(lumalib.LumaException):
+        lumalib.LumaQuantizer()
+
+
+@pytest.mark.parametrize("ptf,bits,lmax,lmin", [("PQ", 11, 1e4, 0.005), ("PQ", 10, 1000.0, 0.01), ("PQ", 12, 1e4, 0.005),
+                                                ("PQ", 8, 1e4, 0.005), ("LOG", 12, 1e4, 0.005), ("LOG", 11, 1e4, 0.005),
+                                                ("PSI", 11, 1e4, 0.005), ("PSI", 10, 1e4, 0.005), ("PSI", 8, 1e4, 0.005),
+                                                ("JND_HDRVDP", 12, 1e4, 0.005), ("JND_HDRVDP", 9, 1e4, 0.005),
+                                                ("LINEAR", 11, 1e4, 0.005), ("LINEAR", 11, 400.0, 0.005),
+                                                ("PQ", 16, 1e4, 0.005)])
+def test_build_lut_equals_oracle(lumalib, po, golden, ptf, bits, lmax, lmin):
+    lut = lumalib.build_lut(ptf, bits, lmax, lmin)
+    o = po.Oracle().setQuantizer(ptf, bits, "LUV", 8, lmax, lmin)
+    assert bits_equal(lut, o.getMapping())
+    key = f"{ptf}:{bits}:{lmax:g}:{lmin:g}"
+    if key in golden["lut"]:
+        assert "%08x" % po.fnv1a32(lut) == golden["lut"][key]
+
+
+def _float_of_key(k):
+    k = np.asarray(k, dtype=np.uint64)
+    b = np.where(k & 0x80000000, k ^ 0x80000000, (~k) & 0xFFFFFFFF).astype(np.uint32)
+    return b.view(np.float32)
+
+
+@pytest.mark.parametrize("ptf,bits", [("PQ", 11), ("PQ", 10), ("PQ", 12), ("LOG", 12), ("PSI", 11), ("JND_HDRVDP", 12),
+                                      ("LINEAR", 11), ("LINEAR", 12), ("PQ", 8)])
+def test_thresholds_pin_reference_decision(lumalib, po, ptf, bits):
+    """code(T_k) == k and code(pred(T_k)) == k-1 for every k, with the oracle's quantize."""
+    lut = lumalib.build_lut(ptf, bits)
+    thr = np.empty(lut.size - 1, dtype=np.uint32)
+    assert lumalib.lib().lumacu_derive_thresholds(lut.ctypes.data, lut.size, thr.ctypes.data) == 1
+    assert np.all(np.diff(thr.astype(np.int64)) > 0)
+    o = po.Oracle().setQuantizer(ptf, bits, "LUV", 8)
+    at, below = _float_of_key(thr), _float_of_key(thr - 1)
+    k = np.arange(1, lut.size)
+    step = max(1, k.size // 512)  # the scalar ctypes oracle is slow; sample + both ends
+    sel = np.unique(np.concatenate([k[::step] - 1, np.arange(0, 8), np.arange(k.size - 8, k.size)]))
+    for i in sel:
+        assert o.quantize(at[i], 0) == k[i]
+        assert o.quantize(below[i], 0) == k[i] - 1
+    if po.reference_available():
+        ref = po.Reference(ptf=ptf, ptfBitDepth=bits)
+        assert np.array_equal(ref.quantize_n(at, 0), k.astype(np.float32))
+        assert np.array_equal(ref.quantize_n(below, 0), (k - 1).astype(np.float32))
+        ref.close()
+    sh, base, nb, wk = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert lumalib.lib().lumacu_plan_buckets(thr.ctypes.data, thr.size, C.byref(sh), C.byref(base), C.byref(nb),
+                                             C.byref(wk)) == 1
+    assert 1 <= nb.value <= 8192 and wk.value >= 1
+    buckets = (thr >> sh.value) - base.value
+    assert buckets.min() == 0 and buckets.max() == nb.value - 1
+    assert np.bincount(buckets).max() == wk.value
+
+
+def test_thresholds_refuse_non_monotone_lut(lumalib):
+    lut = lumalib.build_lut("PQ", 8).copy()
+    thr = np.empty(lut.size - 1, dtype=np.uint32)
+    lut[10] = lut[9]
+    assert lumalib.lib().lumacu_derive_thresholds(lut.ctypes.data, lut.size, thr.ctypes.data) == 0
+    lut = lumalib.build_lut("PQ", 8).copy()
+    lut[100] = np.nan
+    assert lumalib.lib().lumacu_derive_thresholds(lut.ctypes.data, lut.size, thr.ctypes.data) == 0
+
+
+def test_build_lut_errors(lumalib):
+    with pytest.raises(lumalib.LumaException, match="INVALID_ARGUMENT"):
+        lumalib.build_lut(9, 8)
+    out = np.empty(4, dtype=np.float32)
+    assert lumalib.lib().lumacu_build_lut(1, 8, 1e4, 0.005, out.ctypes.data, out.size) == 1
+
+
+def test_geometry_helpers(lumalib, po):
+    for w in (2, 6, 62, 64, 1280, 1920, 3840):
+        for profile in range(4):
+            assert lumalib.vpx_strides(w, profile) == po.vpx_strides(w, profile)
+            assert lumalib.plane_dims(w, 10, profile) == po.plane_dims(w, 10, profile)
+
+
+def test_frame_shards():
+    from lumahdrv_b200.shard import frame_shard
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            got = [frame_shard(n, r, world) for r in range(world)]
+            assert sum(len(g) for g in got) == n
+            assert sorted(i for g in got for i in g) == list(range(n))
+            assert max(len(g) for g in got) - min(len(g) for g in got) <= 1
