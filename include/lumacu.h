@@ -26,7 +26,9 @@
  *    (src/luma_encoder.cpp:121-128,265-269).
  *  - "_dev" entry points take device pointers and a cudaStream_t (passed as
  *    void*) and are asynchronous; the others take host pointers, stage through
- *    pinned buffers and return when the result is in host memory.
+ *    pinned buffers and return when the result is in host memory.  A NULL
+ *    stream selects the context's own (non-blocking) stream; to launch on the
+ *    CUDA default stream pass cudaStreamLegacy (0x1) or cudaStreamPerThread (0x2).
  *  - results are bit-identical to the reference CPU path for the integer
  *    planes and for the decoded floats (see DESIGN.md for the one documented
  *    libm dependency: CS_YCBCR calls powf per pixel).
@@ -203,6 +205,14 @@ uint64_t lumacu_launch_count(const lumacu_ctx *ctx);
  * the LUT (LUT not strictly increasing). */
 int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift,
                        uint32_t *walk);
+
+/* Kernel selection.  path 0 (default): use the tuned kernels (packed fp32x2 math, shared-memory
+ * search tables) whenever their preconditions hold, the generic kernels otherwise; path 1: always
+ * the generic kernels (a literal transcription of the reference loops; used by the tests to
+ * cross-check the two).  Both produce identical bits. */
+int lumacu_set_kernel_path(lumacu_ctx *ctx, int path);
+/* 1 if the last encode/decode launch on this context ran a tuned kernel, 0 if generic. */
+int lumacu_last_kernel_path(const lumacu_ctx *ctx);
 
 #ifdef __cplusplus
 }

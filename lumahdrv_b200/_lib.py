@@ -41,7 +41,7 @@ class FrameStats(C.Structure):
 def build_library(force: bool = False) -> Path:
     """Compile liblumacu.so for sm_100a (nvcc cross-compiles without a GPU)."""
     if force or not LIB_PATH.exists():
-        subprocess.run(["make", "-C", str(CSRC_DIR)] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
+        subprocess.run(["make", "-j", "8", "-C", str(CSRC_DIR)] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -83,6 +83,8 @@ SIGNATURES = {
     "lumacu_transform_color_space_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
     "lumacu_quantize_dev": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint, _P]),
     "lumacu_dequantize_dev": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint, _P]),
+    "lumacu_set_kernel_path": (C.c_int, [_P, C.c_int]),
+    "lumacu_last_kernel_path": (C.c_int, [_P]),
     "lumacu_launch_count": (C.c_uint64, [_P]),
     "lumacu_search_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]),

@@ -16,29 +16,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "luma_kernels_decl.cuh"
 #include "powf_glibc.cuh"
 
 namespace lumacu {
-
-enum { CS_LUV = 0, CS_RGB = 1, CS_YCBCR = 2, CS_XYZ = 3 };
-enum { SEARCH_BUCKET = 0, SEARCH_BINARY = 1, SEARCH_LITERAL = 2 };
-
-/* Quantizer state as the kernels see it (device pointers into the context). */
-struct QuantDev {
-    const float *lut;       /* code -> luminance, max_val + 1 entries (reference m_mapping) */
-    const uint32_t *thr;    /* ordered keys of the max_val decision thresholds + pad sentinels */
-    const uint16_t *bucket; /* first candidate code per key bucket (SEARCH_BUCKET) */
-    uint32_t max_val;
-    uint32_t max_val_color;
-    float max_val_f;
-    float max_val_color_f;
-    float l_max;
-    int search_mode;
-    uint32_t shift, base, nbm1, walk; /* bucket = clamp(key >> shift, base, base + nbm1) - base */
-    uint32_t thr_count;               /* max_val + pad */
-    uint32_t smem_tables;             /* 1: stage thr (+bucket) in shared memory; 0: read from global */
-    uint32_t smem_lut;                /* decode: 1 = stage the LUT in shared memory */
-};
 
 /* ---- NaN-aware compare-selects ------------------------------------------------ */
 __device__ __forceinline__ float min_nan(float a, float b)
@@ -234,10 +215,9 @@ __device__ __forceinline__ void color_inverse(float c0, ChromaInv ch, float l_ma
 template <bool POSITIVE>
 __device__ __forceinline__ uint32_t ordered_key(float v)
 {
-    uint32_t b = __float_as_uint(v);
-    if (POSITIVE) /* v > 0 or the canonical (positive) NaN, which sorts above +Inf */
-        return b ^ 0x80000000u;
-    uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    (void)POSITIVE; /* kept for the call sites; the general transform is always used (see encode_kernel) */
+    const uint32_t b = __float_as_uint(v);
+    const uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
     return (v != v) ? 0xFFFFFFFFu : k; /* the reference maps every NaN to max_val */
 }
 

@@ -1,0 +1,47 @@
+/*
+ * luma_dispatch.h -- host-visible table of the kernel instantiations.
+ *
+ * The kernels are compiled in one translation unit per colour space (luma_kern_tu.cu built with
+ * -DLUMA_TU_CS=<0..3> and -DLUMA_TU_FAST=<0|1>) so that the build parallelises; lumacu.cu picks an
+ * instantiation through these getters and launches it.
+ */
+#pragma once
+
+#include "luma_kernels_decl.cuh"
+
+namespace lumacu {
+
+typedef void (*enc_fn)(const EncArgs);
+typedef void (*dec_fn)(const DecArgs);
+
+/* generic kernels: any colour space / profile / alignment / search mode */
+#define LUMA_DECL_GENERIC(CSV)                                         \
+    enc_fn get_encode_generic_cs##CSV(bool sub, int bytes, bool vec);  \
+    dec_fn get_decode_generic_cs##CSV(bool sub, int bytes, bool vec);
+LUMA_DECL_GENERIC(0)
+LUMA_DECL_GENERIC(1)
+LUMA_DECL_GENERIC(2)
+LUMA_DECL_GENERIC(3)
+#undef LUMA_DECL_GENERIC
+
+/* tuned kernels (luma_fast.cuh); walk is the bucket walk length the search was planned with.
+ * Return NULL when there is no instantiation for the request. */
+#define LUMA_DECL_FAST(CSV)                                          \
+    enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk);   \
+    dec_fn get_decode_fast_cs##CSV(bool sub, int bytes);
+LUMA_DECL_FAST(0)
+LUMA_DECL_FAST(1)
+LUMA_DECL_FAST(2)
+LUMA_DECL_FAST(3)
+#undef LUMA_DECL_FAST
+
+/* element-wise API kernels (compiled in the CS 1 generic unit) */
+void launch_transform(int cs, bool fwd, unsigned blocks, cudaStream_t st, float *c0, float *c1, float *c2, size_t n,
+                      float sc, float l_max);
+void launch_quantize(unsigned blocks, size_t smem, cudaStream_t st, const QuantDev &q, const float *in, float *out,
+                     size_t n, int use_lut);
+void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, const float *in, float *out, size_t n,
+                       int use_lut);
+const void *quantize_kernel_ptr();
+
+} // namespace lumacu

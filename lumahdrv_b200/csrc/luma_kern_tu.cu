@@ -1,0 +1,124 @@
+/*
+ * luma_kern_tu.cu -- one kernel translation unit; built eight times:
+ *   -DLUMA_TU_CS=<0..3>   colour space (CS_LUV, CS_RGB, CS_YCBCR, CS_XYZ)
+ *   -DLUMA_TU_FAST=<0|1>  0: generic kernels (luma_kernels.cuh), 1: tuned kernels (luma_fast.cuh)
+ * so that `make -j` compiles the instantiations in parallel.  Each unit only exports host-side
+ * getters (luma_dispatch.h); lumacu.cu launches what they return.
+ */
+#ifndef LUMA_TU_CS
+#error "build with -DLUMA_TU_CS=<0..3> -DLUMA_TU_FAST=<0|1>"
+#endif
+
+#include "luma_dispatch.h"
+
+#if !LUMA_TU_FAST && LUMA_TU_CS == 1
+#define LUMA_TU_ELEMENTWISE 1 /* the element-wise API kernels live in this unit only */
+#endif
+
+#if LUMA_TU_FAST
+#include "luma_fast.cuh"
+#else
+#include "luma_kernels.cuh"
+#endif
+
+#define LUMA_CAT2(a, b) a##b
+#define LUMA_CAT(a, b) LUMA_CAT2(a, b)
+
+namespace lumacu {
+
+constexpr int kCS = LUMA_TU_CS;
+
+#if !LUMA_TU_FAST
+
+enc_fn LUMA_CAT(get_encode_generic_cs, LUMA_TU_CS)(bool sub, int bytes, bool vec)
+{
+    if (sub) {
+        if (bytes == 2)
+            return vec ? encode_kernel<kCS, true, 2, true> : encode_kernel<kCS, true, 2, false>;
+        return vec ? encode_kernel<kCS, true, 1, true> : encode_kernel<kCS, true, 1, false>;
+    }
+    if (bytes == 2)
+        return vec ? encode_kernel<kCS, false, 2, true> : encode_kernel<kCS, false, 2, false>;
+    return vec ? encode_kernel<kCS, false, 1, true> : encode_kernel<kCS, false, 1, false>;
+}
+
+dec_fn LUMA_CAT(get_decode_generic_cs, LUMA_TU_CS)(bool sub, int bytes, bool vec)
+{
+    if (sub) {
+        if (bytes == 2)
+            return vec ? decode_kernel<kCS, true, 2, true> : decode_kernel<kCS, true, 2, false>;
+        return vec ? decode_kernel<kCS, true, 1, true> : decode_kernel<kCS, true, 1, false>;
+    }
+    if (bytes == 2)
+        return vec ? decode_kernel<kCS, false, 2, true> : decode_kernel<kCS, false, 2, false>;
+    return vec ? decode_kernel<kCS, false, 1, true> : decode_kernel<kCS, false, 1, false>;
+}
+
+#if LUMA_TU_CS == 1
+/* the element-wise API kernels live in one unit only */
+void launch_transform(int cs, bool fwd, unsigned blocks, cudaStream_t st, float *c0, float *c1, float *c2, size_t n,
+                      float sc, float l_max)
+{
+#define LAUNCH_T(CSV)                                                                   \
+    if (fwd)                                                                            \
+        transform_kernel<CSV, true><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, l_max); \
+    else                                                                                \
+        transform_kernel<CSV, false><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, l_max);
+    switch (cs) {
+    case CS_LUV: LAUNCH_T(CS_LUV) break;
+    case CS_RGB: LAUNCH_T(CS_RGB) break;
+    case CS_YCBCR: LAUNCH_T(CS_YCBCR) break;
+    default: LAUNCH_T(CS_XYZ) break;
+    }
+#undef LAUNCH_T
+}
+
+void launch_quantize(unsigned blocks, size_t smem, cudaStream_t st, const QuantDev &q, const float *in, float *out,
+                     size_t n, int use_lut)
+{
+    quantize_kernel<<<blocks, kThreads, smem, st>>>(q, in, out, n, use_lut);
+}
+
+void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, const float *in, float *out, size_t n,
+                       int use_lut)
+{
+    dequantize_kernel<<<blocks, kThreads, 0, st>>>(q, in, out, n, use_lut);
+}
+
+const void *quantize_kernel_ptr() { return (const void *)quantize_kernel; }
+#endif
+
+#else /* LUMA_TU_FAST */
+
+template <bool SUB, int BYTES>
+static enc_fn pick_walk(int walk)
+{
+#if LUMA_TU_CS == 0
+    /* the headline colour space gets the exact walk length */
+    if (walk <= 1)
+        return encode_fast_kernel<kCS, SUB, BYTES, 1>;
+    if (walk == 2)
+        return encode_fast_kernel<kCS, SUB, BYTES, 2>;
+#endif
+    if (walk <= 4)
+        return encode_fast_kernel<kCS, SUB, BYTES, 4>;
+    return nullptr;
+}
+
+enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk)
+{
+    if (sub)
+        return bytes == 2 ? pick_walk<true, 2>(walk) : pick_walk<true, 1>(walk);
+    return bytes == 2 ? pick_walk<false, 2>(walk) : pick_walk<false, 1>(walk);
+}
+
+dec_fn LUMA_CAT(get_decode_fast_cs, LUMA_TU_CS)(bool sub, int bytes)
+{
+    if (sub)
+        return bytes == 2 ? decode_fast_kernel<kCS, true, 2> : decode_fast_kernel<kCS, true, 1>;
+    return bytes == 2 ? decode_fast_kernel<kCS, false, 2> : decode_fast_kernel<kCS, false, 1>;
+}
+
+#endif
+
+} // namespace lumacu

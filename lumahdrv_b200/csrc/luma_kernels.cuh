@@ -21,53 +21,9 @@
 #pragma once
 
 #include "luma_device.cuh"
+#include "luma_kernels_decl.cuh"
 
 namespace lumacu {
-
-constexpr int kThreads = 256;
-
-struct StatsPartial {
-    double sum;
-    float mx;
-    float mn;
-};
-
-struct FrameStatsDev { /* same layout as lumacu_frame_stats */
-    double sum;
-    float mx;
-    float mn;
-};
-
-struct EncArgs {
-    QuantDev q;
-    const float *rgb;
-    float *rgb_out; /* nullable: colour-transformed frame (reference's in-place side effect) */
-    size_t rgb_plane_stride; /* floats between the R, G, B planes */
-    size_t rgb_frame_stride; /* floats between frames */
-    size_t out_plane_stride, out_frame_stride;
-    uint32_t w, h;
-    uint8_t *plane[3];
-    int32_t stride[3];
-    size_t plane_frame_stride[3];
-    float sc;
-    int prescale; /* sc != 1 */
-    StatsPartial *partial; /* [frames][gridDim.x], nullable together with stats */
-    uint32_t *counter;     /* [frames] */
-    FrameStatsDev *stats;  /* [frames] */
-};
-
-struct DecArgs {
-    QuantDev q;
-    const uint8_t *plane[3];
-    int32_t stride[3];
-    size_t plane_frame_stride[3];
-    float *rgb;
-    size_t rgb_plane_stride;
-    size_t rgb_frame_stride;
-    uint32_t w, h;
-    float sc;
-    int prescale;
-};
 
 /* ---- streaming global accesses (each byte is touched once) --------------------- */
 __device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
@@ -278,7 +234,10 @@ __global__ void __launch_bounds__(kThreads) encode_kernel(const EncArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SearchCtx s = make_search_ctx(a.q, smem_raw);
     constexpr bool LUT_ALL = (CS == CS_RGB || CS == CS_XYZ); /* every plane goes through the LUT search */
-    constexpr bool POS = (CS == CS_LUV || CS == CS_XYZ);     /* searched values are > 0 or canonical NaN */
+    /* always the full key transform with its explicit NaN test: the shortcut `bits ^ 0x80000000` for
+     * positive values is compiled into a float negation (FADD -x, -0), which canonicalises a NaN instead
+     * of flipping its sign bit and would send NaN to code 0 instead of max_val */
+    constexpr bool POS = false;
 
     const uint32_t frame = blockIdx.y;
     const float *rgb = a.rgb + (size_t)frame * a.rgb_frame_stride;
@@ -553,7 +512,8 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
     }
 }
 
-/* ====================== element-wise API kernels ================================= */
+#ifdef LUMA_TU_ELEMENTWISE
+/* ====================== element-wise API kernels (one translation unit only) ===== */
 /* LumaQuantizer::transformColorSpace in place on a planar frame of n pixels. */
 template <int CS, bool FWD>
 __global__ void __launch_bounds__(kThreads) transform_kernel(float *c0, float *c1, float *c2, size_t n, float sc, float l_max)
@@ -608,5 +568,7 @@ __global__ void __launch_bounds__(kThreads) dequantize_kernel(const QuantDev q, 
         out[i] = r;
     }
 }
+
+#endif /* LUMA_TU_ELEMENTWISE */
 
 } // namespace lumacu

@@ -1,0 +1,80 @@
+/*
+ * luma_kernels_decl.cuh -- argument blocks shared by the kernels and the host launcher.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace lumacu {
+
+enum { CS_LUV = 0, CS_RGB = 1, CS_YCBCR = 2, CS_XYZ = 3 };
+enum { SEARCH_BUCKET = 0, SEARCH_BINARY = 1, SEARCH_LITERAL = 2 };
+
+/* Quantizer state as the kernels see it (device pointers into the context). */
+struct QuantDev {
+    const float *lut;       /* code -> luminance, max_val + 1 entries (reference m_mapping) */
+    const uint32_t *thr;    /* ordered keys of the max_val decision thresholds + pad sentinels */
+    const uint16_t *bucket; /* first candidate code per key bucket (SEARCH_BUCKET) */
+    uint32_t max_val;
+    uint32_t max_val_color;
+    float max_val_f;
+    float max_val_color_f;
+    float l_max;
+    int search_mode;
+    uint32_t shift, base, nbm1, walk; /* bucket = clamp(key >> shift, base, base + nbm1) - base */
+    uint32_t thr_count;               /* max_val + pad */
+    uint32_t smem_tables;             /* 1: stage thr (+bucket) in shared memory; 0: read from global */
+    uint32_t smem_lut;                /* decode: 1 = stage the LUT in shared memory */
+    const float *ctab;                /* chroma code -> u'/v' (LUV) or Cb/Cr (YCBCR), max_val_color + 1 entries */
+};
+
+constexpr int kThreads = 256;
+
+struct StatsPartial {
+    double sum;
+    float mx;
+    float mn;
+};
+
+struct FrameStatsDev { /* same layout as lumacu_frame_stats */
+    double sum;
+    float mx;
+    float mn;
+};
+
+struct EncArgs {
+    QuantDev q;
+    const float *rgb;
+    float *rgb_out; /* nullable: colour-transformed frame (reference's in-place side effect) */
+    size_t rgb_plane_stride; /* floats between the R, G, B planes */
+    size_t rgb_frame_stride; /* floats between frames */
+    size_t out_plane_stride, out_frame_stride;
+    uint32_t w, h;
+    uint8_t *plane[3];
+    int32_t stride[3];
+    size_t plane_frame_stride[3];
+    float sc;
+    int prescale; /* sc != 1 */
+    StatsPartial *partial; /* [frames][gridDim.x], nullable together with stats */
+    uint32_t *counter;     /* [frames] */
+    FrameStatsDev *stats;  /* [frames] */
+    float2 nz;             /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
+};
+
+struct DecArgs {
+    QuantDev q;
+    const uint8_t *plane[3];
+    int32_t stride[3];
+    size_t plane_frame_stride[3];
+    float *rgb;
+    size_t rgb_plane_stride;
+    size_t rgb_frame_stride;
+    uint32_t w, h;
+    float sc;
+    int prescale;
+    float2 nz; /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
+};
+
+} // namespace lumacu

@@ -24,7 +24,7 @@
 #include <string>
 #include <vector>
 
-#include "luma_kernels.cuh"
+#include "luma_dispatch.h"
 
 using namespace lumacu;
 
@@ -73,6 +73,8 @@ struct lumacu_ctx {
     int sm_count = 0;
     std::string err;
     uint64_t launches = 0;
+    bool force_generic = false; /* tests: run the literal kernels */
+    bool last_fast = false;     /* the last encode/decode launch used a tuned kernel */
 
     /* quantizer */
     bool configured = false;
@@ -81,6 +83,8 @@ struct lumacu_ctx {
     std::vector<float> h_lut;
     DeviceBuffer d_tables; /* lut | thr | bucket */
     size_t smem_enc = 0, smem_dec = 0;
+    size_t smem_dec_fast = 0; /* lut + chroma table; 0 = fast decode unavailable */
+    bool fast_enc_ok = false;
 
     /* stats workspace */
     DeviceBuffer d_partial, d_counter;
@@ -448,15 +452,33 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
             }
         }
     }
-    const uint32_t pad = std::max(walk, 2u);
+    const uint32_t pad = std::max(walk, 4u); /* the tuned kernels read up to 4 thresholds from any bucket head */
     const uint32_t thr_count = (mode == SEARCH_LITERAL) ? 0u : max_val + pad;
     if (mode != SEARCH_LITERAL)
         thr.resize(thr_count, 0xFFFFFFFFu);
 
-    /* one device allocation: lut | thr | bucket */
+    /* chroma code -> first chroma term of the inverse transform, with the reference's own expressions
+     * (dequantize: src/luma_quantizer.cpp:261; Lu'v': :406-407).  Host float arithmetic, no contraction. */
+    std::vector<float> ctab;
+    if (color_space == CS_LUV || color_space == CS_YCBCR) {
+        ctab.resize((size_t)max_val_color + 1);
+        const float mc = (float)max_val_color;
+        for (uint32_t i = 0; i <= max_val_color; i++) {
+            volatile float c = (float)i / mc;
+            c = (c < 1e-10f) ? 1e-10f : c; /* std::max(val/maxC, 1e-10f) */
+            if (color_space == CS_LUV) {
+                volatile float t = c * 255.0f;
+                c = t / 410.0f;
+            }
+            ctab[i] = c;
+        }
+    }
+
+    /* one device allocation: lut | thr | bucket | ctab */
     const size_t off_thr = ((size_t)lut_len * 4 + 15) & ~(size_t)15;
     const size_t off_bucket = (off_thr + (size_t)thr_count * 4 + 15) & ~(size_t)15;
-    const size_t total = off_bucket + bucket.size() * 2 + 16;
+    const size_t off_ctab = (off_bucket + bucket.size() * 2 + 15) & ~(size_t)15;
+    const size_t total = off_ctab + ctab.size() * 4 + 16;
     int rc = reserve(ctx, ctx->d_tables, total);
     if (rc)
         return rc;
@@ -468,11 +490,14 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
         CU_TRY(ctx, cudaMemcpy(d + off_thr, thr.data(), (size_t)thr_count * 4, cudaMemcpyHostToDevice));
     if (!bucket.empty())
         CU_TRY(ctx, cudaMemcpy(d + off_bucket, bucket.data(), bucket.size() * 2, cudaMemcpyHostToDevice));
+    if (!ctab.empty())
+        CU_TRY(ctx, cudaMemcpy(d + off_ctab, ctab.data(), ctab.size() * 4, cudaMemcpyHostToDevice));
 
     QuantDev q{};
     q.lut = (const float *)d;
     q.thr = (const uint32_t *)(d + off_thr);
     q.bucket = (const uint16_t *)(d + off_bucket);
+    q.ctab = ctab.empty() ? nullptr : (const float *)(d + off_ctab);
     q.max_val = max_val;
     q.max_val_color = max_val_color;
     q.max_val_f = (float)max_val;
@@ -495,6 +520,14 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
     if (smem_dec > kMaxSmemLut)
         smem_dec = 0;
     q.smem_lut = smem_dec ? 1u : 0u;
+
+    /* tuned kernels: bucket search out of shared memory (encode); LUT + chroma table in shared memory (decode) */
+    size_t smem_dec_fast = ((size_t)lut_len + ctab.size()) * 4;
+    if (smem_dec_fast > kMaxSmemLut)
+        smem_dec_fast = 0;
+    /* (the tuned search also wants every threshold to be a positive float: key > key(+0)) */
+    ctx->fast_enc_ok = (mode == SEARCH_BUCKET && smem_enc != 0 && thr[0] > 0x80000000u);
+    ctx->smem_dec_fast = smem_dec_fast;
 
     ctx->q = q;
     ctx->smem_enc = smem_enc;
@@ -520,52 +553,55 @@ extern "C" int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_
     return LUMACU_OK;
 }
 
+extern "C" int lumacu_set_kernel_path(lumacu_ctx *ctx, int path)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (path != 0 && path != 1)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_kernel_path: path %d not in {0,1}", path);
+    ctx->force_generic = (path == 1);
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_last_kernel_path(const lumacu_ctx *ctx) { return (ctx && ctx->last_fast) ? 1 : 0; }
+
 /* ================================ launches ============================================ */
 namespace {
 
-typedef void (*enc_fn)(const EncArgs);
-typedef void (*dec_fn)(const DecArgs);
-
-template <int CS>
-enc_fn pick_enc_cs(bool sub, int bytes, bool vec)
-{
-    if (sub) {
-        if (bytes == 2)
-            return vec ? encode_kernel<CS, true, 2, true> : encode_kernel<CS, true, 2, false>;
-        return vec ? encode_kernel<CS, true, 1, true> : encode_kernel<CS, true, 1, false>;
-    }
-    if (bytes == 2)
-        return vec ? encode_kernel<CS, false, 2, true> : encode_kernel<CS, false, 2, false>;
-    return vec ? encode_kernel<CS, false, 1, true> : encode_kernel<CS, false, 1, false>;
-}
 enc_fn pick_enc(int cs, bool sub, int bytes, bool vec)
 {
     switch (cs) {
-    case CS_LUV: return pick_enc_cs<CS_LUV>(sub, bytes, vec);
-    case CS_RGB: return pick_enc_cs<CS_RGB>(sub, bytes, vec);
-    case CS_YCBCR: return pick_enc_cs<CS_YCBCR>(sub, bytes, vec);
-    default: return pick_enc_cs<CS_XYZ>(sub, bytes, vec);
+    case CS_LUV: return get_encode_generic_cs0(sub, bytes, vec);
+    case CS_RGB: return get_encode_generic_cs1(sub, bytes, vec);
+    case CS_YCBCR: return get_encode_generic_cs2(sub, bytes, vec);
+    default: return get_encode_generic_cs3(sub, bytes, vec);
     }
-}
-template <int CS>
-dec_fn pick_dec_cs(bool sub, int bytes, bool vec)
-{
-    if (sub) {
-        if (bytes == 2)
-            return vec ? decode_kernel<CS, true, 2, true> : decode_kernel<CS, true, 2, false>;
-        return vec ? decode_kernel<CS, true, 1, true> : decode_kernel<CS, true, 1, false>;
-    }
-    if (bytes == 2)
-        return vec ? decode_kernel<CS, false, 2, true> : decode_kernel<CS, false, 2, false>;
-    return vec ? decode_kernel<CS, false, 1, true> : decode_kernel<CS, false, 1, false>;
 }
 dec_fn pick_dec(int cs, bool sub, int bytes, bool vec)
 {
     switch (cs) {
-    case CS_LUV: return pick_dec_cs<CS_LUV>(sub, bytes, vec);
-    case CS_RGB: return pick_dec_cs<CS_RGB>(sub, bytes, vec);
-    case CS_YCBCR: return pick_dec_cs<CS_YCBCR>(sub, bytes, vec);
-    default: return pick_dec_cs<CS_XYZ>(sub, bytes, vec);
+    case CS_LUV: return get_decode_generic_cs0(sub, bytes, vec);
+    case CS_RGB: return get_decode_generic_cs1(sub, bytes, vec);
+    case CS_YCBCR: return get_decode_generic_cs2(sub, bytes, vec);
+    default: return get_decode_generic_cs3(sub, bytes, vec);
+    }
+}
+enc_fn pick_enc_fast(int cs, bool sub, int bytes, int walk)
+{
+    switch (cs) {
+    case CS_LUV: return get_encode_fast_cs0(sub, bytes, walk);
+    case CS_RGB: return get_encode_fast_cs1(sub, bytes, walk);
+    case CS_YCBCR: return get_encode_fast_cs2(sub, bytes, walk);
+    default: return get_encode_fast_cs3(sub, bytes, walk);
+    }
+}
+dec_fn pick_dec_fast(int cs, bool sub, int bytes)
+{
+    switch (cs) {
+    case CS_LUV: return get_decode_fast_cs0(sub, bytes);
+    case CS_RGB: return get_decode_fast_cs1(sub, bytes);
+    case CS_YCBCR: return get_decode_fast_cs2(sub, bytes);
+    default: return get_decode_fast_cs3(sub, bytes);
     }
 }
 
@@ -652,6 +688,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     a.h = h;
     a.sc = pre_scaling;
     a.prescale = (pre_scaling != 1.0f) ? 1 : 0;
+    a.nz = make_float2(-0.0f, -0.0f);
     bool vec = (w % 4 == 0) && aligned(d_rgb, 16) && (a.rgb_frame_stride % 4 == 0) && (a.rgb_plane_stride % 4 == 0) &&
                (!d_rgb_out || aligned(d_rgb_out, 16));
     for (int p = 0; p < 3; p++) {
@@ -661,7 +698,13 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
         const size_t al = (size_t)((p && sub) ? 2 : 4) * bytes; /* bytes stored per thread and row */
         vec = vec && aligned(d_planes[p], al) && (strides[p] % al == 0) && (a.plane_frame_stride[p] % al == 0);
     }
-    enc_fn fn = pick_enc(ctx->color_space, sub, bytes, vec);
+    enc_fn fn = nullptr;
+    const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
+    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic)
+        fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk);
+    ctx->last_fast = fn != nullptr;
+    if (!fn)
+        fn = pick_enc(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
     uint32_t gx = 1;
     rc = grid_for(ctx, (const void *)fn, ctx->smem_enc, ntiles, n_frames, &gx);
@@ -723,6 +766,7 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     a.h = h;
     a.sc = pre_scaling;
     a.prescale = (pre_scaling != 1.0f) ? 1 : 0;
+    a.nz = make_float2(-0.0f, -0.0f);
     bool vec = (w % 4 == 0) && aligned(d_rgb, 16) && (a.rgb_frame_stride % 4 == 0) && (a.rgb_plane_stride % 4 == 0);
     for (int p = 0; p < 3; p++) {
         a.plane[p] = d_planes[p];
@@ -731,13 +775,22 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
         const size_t al = (size_t)((p && sub) ? 2 : 4) * bytes;
         vec = vec && aligned(d_planes[p], al) && (strides[p] % al == 0) && (a.plane_frame_stride[p] % al == 0);
     }
-    dec_fn fn = pick_dec(ctx->color_space, sub, bytes, vec);
+    dec_fn fn = nullptr;
+    size_t smem = ctx->smem_dec;
+    const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
+    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic) {
+        fn = pick_dec_fast(ctx->color_space, sub, bytes);
+        smem = ctx->smem_dec_fast;
+    }
+    ctx->last_fast = fn != nullptr;
+    if (!fn)
+        fn = pick_dec(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
     uint32_t gx = 1;
-    rc = grid_for(ctx, (const void *)fn, ctx->smem_dec, ntiles, n_frames, &gx);
+    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, &gx);
     if (rc)
         return rc;
-    fn<<<dim3(gx, n_frames), kThreads, ctx->smem_dec, st>>>(a);
+    fn<<<dim3(gx, n_frames), kThreads, smem, st>>>(a);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -760,18 +813,7 @@ extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame,
     const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 16);
     float *c0 = d_frame, *c1 = d_frame + n, *c2 = d_frame + 2 * n;
     const float L = ctx->q.l_max;
-#define LAUNCH_T(CSV)                                                                        \
-    if (to_cs)                                                                               \
-        transform_kernel<CSV, true><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, L);      \
-    else                                                                                     \
-        transform_kernel<CSV, false><<<blocks, kThreads, 0, st>>>(c0, c1, c2, n, sc, L);
-    switch (ctx->color_space) {
-    case CS_LUV: LAUNCH_T(CS_LUV) break;
-    case CS_RGB: LAUNCH_T(CS_RGB) break;
-    case CS_YCBCR: LAUNCH_T(CS_YCBCR) break;
-    default: LAUNCH_T(CS_XYZ) break;
-    }
-#undef LAUNCH_T
+    launch_transform(ctx->color_space, to_cs != 0, blocks, st, c0, c1, c2, n, sc, L);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -794,11 +836,11 @@ extern "C" int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_quantize_dev: NULL pointer");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    const void *fn = (const void *)quantize_kernel;
+    const void *fn = quantize_kernel_ptr();
     if (ctx->smem_enc > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_enc));
     const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 4);
-    quantize_kernel<<<blocks, kThreads, ctx->smem_enc, st>>>(ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
+    launch_quantize(blocks, ctx->smem_enc, st, ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -817,7 +859,7 @@ extern "C" int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
-    dequantize_kernel<<<blocks, kThreads, 0, st>>>(ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
+    launch_dequantize(blocks, st, ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;

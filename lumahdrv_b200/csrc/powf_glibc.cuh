@@ -26,7 +26,7 @@
 namespace lumacu {
 
 /* __powf_log2_data (POWF_LOG2_TABLE_BITS = 4, POWF_SCALE_BITS = 0) */
-__device__ const double2 k_powf_log2_tab[16] = {
+static __device__ const double2 k_powf_log2_tab[16] = {
     {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
     {0x1.49539f0f010bp+0, -0x1.7418b0a1fb77bp-2},  {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
     {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8eap+0, -0x1.97c1d1b3b7afp-3},
@@ -38,7 +38,7 @@ __device__ const double2 k_powf_log2_tab[16] = {
 
 /* __exp2f_data.tab (EXP2F_TABLE_BITS = 5): bits of 2^(i/32) with the exponent
  * contribution i << 47 subtracted */
-__device__ const unsigned long long k_exp2f_tab[32] = {
+static __device__ const unsigned long long k_exp2f_tab[32] = {
     0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
     0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
     0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,

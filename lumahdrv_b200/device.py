@@ -19,8 +19,12 @@ from .luma import Context, LumaQuantizer, plane_dims, vpx_strides
 STATS_DTYPE = np.dtype([("sum", "<f8"), ("max", "<f4"), ("min", "<f4")])
 
 
+CUDA_STREAM_LEGACY = 0x1  # cudaStreamLegacy: the C ABI reads a NULL stream as "the context's own stream"
+
+
 def _stream_ptr(device) -> int:
-    return int(torch.cuda.current_stream(device).cuda_stream)
+    """Handle of torch's current stream; the legacy default stream (handle 0) is passed as cudaStreamLegacy."""
+    return int(torch.cuda.current_stream(device).cuda_stream) or CUDA_STREAM_LEGACY
 
 
 class DeviceTransform:

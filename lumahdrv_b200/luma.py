@@ -98,6 +98,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.lumacu_launch_count(self.handle))
 
+    def set_kernel_path(self, path: int) -> None:
+        """0 = tuned kernels when their preconditions hold (default), 1 = generic kernels only."""
+        check(self._lib.lumacu_set_kernel_path(self.handle, int(path)), self.handle, "lumacu_set_kernel_path")
+
+    @property
+    def last_kernel_path(self) -> int:
+        """1 if the last encode/decode launch ran a tuned kernel, 0 if it ran a generic one."""
+        return int(self._lib.lumacu_last_kernel_path(self.handle))
+
 
 def build_lut(ptf, bitdepth: int, max_lum: float = 10000.0, min_lum: float = 0.005) -> np.ndarray:
     """The table half of LumaQuantizer::setQuantizer (host libm, reference formulas)."""

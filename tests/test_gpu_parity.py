@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 CS = ("LUV", "RGB", "YCBCR", "XYZ")
 FLOAT_ULP_TOL = {"LUV": 0, "RGB": 0, "XYZ": 0, "YCBCR": 1}
+KERNEL_PATHS_SEEN = set()  # (stage, requested path, tuned kernel used)
 
 
 @pytest.fixture(scope="module")
@@ -38,14 +39,40 @@ def check_frame(L, po, frame, enc, o, profile, sc, cs, strides=None):
     enc.initialize(None, w, h)
     assert enc.getParams().profile == profile
     f_gpu, f_cpu = frame.copy(), frame.copy()
+    planes_cpu, avg = o.encode(f_cpu, profile, sc, strides)
+    nbytes = 2 if profile > 1 else 1
+
+    def same_planes(got, what):
+        for p, (a, b, (pw, ph)) in enumerate(zip(got, planes_cpu, po.plane_dims(w, h, profile))):
+            ga, gb = a[:ph, :pw * nbytes], b[:ph, :pw * nbytes]
+            if not np.array_equal(ga, gb):
+                bad = np.argwhere(ga != gb)
+                detail = []
+                for yy, xb in bad[:6]:
+                    xs = int(xb) // nbytes
+                    sub = (p > 0 and profile in (0, 2))
+                    fy, fx = (yy * 2, xs * 2) if sub else (yy, xs)
+                    detail.append(f"(y={yy},x={xs}) got={ga[yy, xb]} ref={gb[yy, xb]} rgb={frame[:, fy, fx].tolist()}"
+                                  f" bits={[hex(v) for v in frame[:, fy, fx].view(np.uint32).tolist()]}")
+                raise AssertionError(f"{what}: plane {p} differs in {len(bad)} bytes: " + "; ".join(detail))
+            assert np.all(a[:, pw * nbytes:] == 0xAB), f"{what}: pitch padding was written"
+
+    # both kernel families (tuned where its preconditions hold, and the generic transcription) without the
+    # reference's in-place side effect, then once more with it (always the generic kernel)
+    for path in (0, 1):
+        enc.m_quant.ctx.set_kernel_path(path)
+        enc.strict_side_effect = False
+        f_in = frame.copy()
+        planes_path = L.alloc_planes(w, h, profile, strides, fill=0xAB)
+        enc.encode(f_in, planes_path)
+        same_planes(planes_path, f"kernel path {path} (tuned={enc.m_quant.ctx.last_kernel_path})")
+        assert bits_equal(f_in, frame), "input frame modified without strict_side_effect"
+        KERNEL_PATHS_SEEN.add(("enc", path, enc.m_quant.ctx.last_kernel_path))
+    enc.m_quant.ctx.set_kernel_path(0)
     planes_gpu = L.alloc_planes(w, h, profile, strides, fill=0xAB)
     enc.strict_side_effect = True
     enc.encode(f_gpu, planes_gpu)
-    planes_cpu, avg = o.encode(f_cpu, profile, sc, strides)
-    nbytes = 2 if profile > 1 else 1
-    for p, (a, b, (pw, ph)) in enumerate(zip(planes_gpu, planes_cpu, po.plane_dims(w, h, profile))):
-        assert np.array_equal(a[:ph, :pw * nbytes], b[:ph, :pw * nbytes]), f"plane {p} differs"
-        assert np.all(a[:, pw * nbytes:] == 0xAB), "pitch padding was written"
+    same_planes(planes_gpu, "strict side effect")
     # the reference's in-place side effect on the caller's frame
     tol = FLOAT_ULP_TOL[cs]
     assert max_ulp(f_gpu, f_cpu) <= tol
@@ -62,11 +89,14 @@ def check_frame(L, po, frame, enc, o, profile, sc, cs, strides=None):
                              profile=profile)
     dec.setParams(dp)
     dec.initialize()
-    out_gpu = dec.decode(planes_cpu, w, h)
     out_cpu = o.decode(planes_cpu, w, h, profile, sc)
-    assert max_ulp(out_gpu, out_cpu) <= tol
-    if tol == 0:
-        assert bits_equal(out_gpu, out_cpu)
+    for path in (1, 0):
+        dec.m_quant.ctx.set_kernel_path(path)
+        out_gpu = dec.decode(planes_cpu, w, h).copy()
+        KERNEL_PATHS_SEEN.add(("dec", path, dec.m_quant.ctx.last_kernel_path))
+        assert max_ulp(out_gpu, out_cpu) <= tol, f"decode kernel path {path}"
+        if tol == 0:
+            assert bits_equal(out_gpu, out_cpu), f"decode kernel path {path}"
     return planes_gpu, out_gpu
 
 
@@ -282,3 +312,11 @@ def test_mean_luminance_warning(L, po):
     enc.warnings.clear()
     enc.encode(np.full((3, 32, 64), 50.0, np.float32))
     assert not enc.warnings
+
+
+def test_zz_both_kernel_families_were_exercised(L):
+    """Runs last in this module: the parity cases above must have hit the tuned AND the generic kernels."""
+    if not KERNEL_PATHS_SEEN:
+        pytest.skip("no parity case ran in this session")
+    assert ("enc", 0, 1) in KERNEL_PATHS_SEEN and ("dec", 0, 1) in KERNEL_PATHS_SEEN, KERNEL_PATHS_SEEN
+    assert ("enc", 1, 0) in KERNEL_PATHS_SEEN and ("dec", 1, 0) in KERNEL_PATHS_SEEN, KERNEL_PATHS_SEEN
