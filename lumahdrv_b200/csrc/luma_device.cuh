@@ -34,6 +34,16 @@ __device__ __forceinline__ float max_nan(float a, float b)
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+/* std::max(0.0f, std::min(1.0f, v)) of the YCbCr inverse (src/luma_quantizer.cpp:453-455).  The C++
+ * library functions are compare-selects -- (v < 1) ? v : 1, then (0 < t) ? t : 0 -- so NaN -> 1.  Both
+ * fmaxf(0, fminf(1, v)) and the literal compare-selects are recognised by the compiler as a saturate
+ * (FADD.SAT), which sends NaN to 0; hence the saturate is written out and NaN is patched explicitly. */
+__device__ __forceinline__ float clamp01_std(float v)
+{
+    const float t = __saturatef(v);
+    return (v != v) ? 1.0f : t;
+}
+
 /* std::max(std::min(v, 1e8f), 1e-4f) (src/luma_quantizer.cpp:284-286,303-305,412-414):
  * NaN in -> NaN out. */
 __device__ __forceinline__ float clamp_xyz(float v) { return max_nan(min_nan(v, 100000000.0f), 0.0001f); }
@@ -192,9 +202,9 @@ __device__ __forceinline__ void color_inverse(float c0, ChromaInv ch, float l_ma
         float green =
             __fdiv_rn(__fsub_rn(__fsub_rn(y, __fmul_rn(0.2627f, red)), __fmul_rn(0.0593f, blue)), 0.6780f);
         /* std::max(0.0f, std::min(1.0f, v)): NaN -> 1 */
-        red = fmaxf(0.0f, fminf(1.0f, red));
-        green = fmaxf(0.0f, fminf(1.0f, green));
-        blue = fmaxf(0.0f, fminf(1.0f, blue));
+        red = clamp01_std(red);
+        green = clamp01_std(green);
+        blue = clamp01_std(blue);
         R = pq_decode(red, l_max);
         G = pq_decode(green, l_max);
         B = pq_decode(blue, l_max);
