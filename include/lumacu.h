@@ -161,6 +161,18 @@ int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profi
 int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
                   uint32_t w, uint32_t h, int profile, float pre_scaling, float *rgb);
 
+/* The two halves of the reference's unfused path, for callers that use them separately:
+ * lumacu_quantize_planes = LumaEncoder::setChannels (src/luma_encoder.cpp:196-201,260-317): `frame` is
+ * ALREADY colour-transformed (e.g. by lumacu_transform_color_space); [2x2 mean,] quantize, pack.
+ * lumacu_dequantize_planes = LumaDecoder::getVpxChannels (src/luma_decoder.cpp:205-240): unpack,
+ * dequantize, [2x2 replicate]; the result still has to go through the inverse colour transform. */
+int lumacu_quantize_planes(lumacu_ctx *ctx, const float *frame, uint32_t w, uint32_t h, int profile,
+                           uint8_t *const planes[3], const int32_t strides[3],
+                           lumacu_frame_stats *stats);
+int lumacu_dequantize_planes(lumacu_ctx *ctx, const uint8_t *const planes[3],
+                             const int32_t strides[3], uint32_t w, uint32_t h, int profile,
+                             float *frame);
+
 /* LumaQuantizer::transformColorSpace(frame, toCs, sc) (src/luma_quantizer.cpp:
  * 267-482): in-place colour transform of a planar f32 frame. */
 int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs,

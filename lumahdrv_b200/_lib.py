@@ -73,6 +73,8 @@ SIGNATURES = {
     "lumacu_encode": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
                                 C.POINTER(FrameStats)]),
     "lumacu_decode": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
+    "lumacu_quantize_planes": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _PP3, _PI3, C.POINTER(FrameStats)]),
+    "lumacu_dequantize_planes": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, _P]),
     "lumacu_transform_color_space": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float]),
     "lumacu_quantize": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint]),
     "lumacu_dequantize": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint]),

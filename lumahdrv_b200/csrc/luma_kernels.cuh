@@ -287,6 +287,8 @@ __global__ void __launch_bounds__(kThreads) encode_kernel(const EncArgs a)
         for (int r = 0; r < 2; ++r) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                if (a.passthrough)
+                    continue; /* LumaEncoder::setChannels: the caller already ran transformColorSpace */
                 float R = c[0][r][i], G = c[1][r][i], B = c[2][r][i];
                 if (a.prescale) {
                     R = __fmul_rn(R, a.sc);
@@ -449,7 +451,13 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
                     c1 = dequantize_chroma((float)cc[0][j], max_c);
                     c2 = dequantize_chroma((float)cc[1][j], max_c);
                 }
-                ChromaInv ci = chroma_inverse<CS>(c1, c2);
+                ChromaInv ci;
+                if (a.passthrough) {
+                    ci.a = c1;
+                    ci.b = c2;
+                } else {
+                    ci = chroma_inverse<CS>(c1, c2);
+                }
                 chr[0][2 * j] = chr[0][2 * j + 1] = chr[1][2 * j] = chr[1][2 * j + 1] = ci;
             }
         } else {
@@ -470,7 +478,12 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
                         c1 = dequantize_chroma((float)cc1[i], max_c);
                         c2 = dequantize_chroma((float)cc2[i], max_c);
                     }
-                    chr[r][i] = chroma_inverse<CS>(c1, c2);
+                    if (a.passthrough) {
+                        chr[r][i].a = c1;
+                        chr[r][i].b = c2;
+                    } else {
+                        chr[r][i] = chroma_inverse<CS>(c1, c2);
+                    }
                 }
             }
         }
@@ -482,6 +495,12 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
             for (int i = 0; i < 4; ++i) {
                 const float c0 = lut[min(code0[r][i], max_val)];
                 float R, G, B;
+                if (a.passthrough) { /* LumaDecoder::getVpxChannels only */
+                    o[0][r][i] = c0;
+                    o[1][r][i] = chr[r][i].a;
+                    o[2][r][i] = chr[r][i].b;
+                    continue;
+                }
                 color_inverse<CS>(c0, chr[r][i], l_max, R, G, B);
                 if (a.prescale) {
                     R = __fdiv_rn(R, a.sc);

@@ -61,6 +61,7 @@ struct EncArgs {
     uint32_t *counter;     /* [frames] */
     FrameStatsDev *stats;  /* [frames] */
     float2 nz;             /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
+    int passthrough;       /* generic kernels: the frame is already colour-transformed (setChannels) */
 };
 
 struct DecArgs {
@@ -75,6 +76,7 @@ struct DecArgs {
     float sc;
     int prescale;
     float2 nz; /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
+    int passthrough; /* generic kernels: stop after dequantisation + chroma replication (getVpxChannels) */
 };
 
 } // namespace lumacu

@@ -22,6 +22,8 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "luma_dispatch.h"
@@ -73,8 +75,10 @@ struct lumacu_ctx {
     int sm_count = 0;
     std::string err;
     uint64_t launches = 0;
+    std::unordered_map<const void *, std::pair<size_t, int>> occupancy; /* kernel -> (smem, blocks per SM) */
     bool force_generic = false; /* tests: run the literal kernels */
     bool last_fast = false;     /* the last encode/decode launch used a tuned kernel */
+    bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
 
     /* quantizer */
     bool configured = false;
@@ -610,18 +614,27 @@ inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) =
 /* persistent grid: resident blocks on the whole chip, capped by the work */
 int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint32_t n_frames, uint32_t *gx)
 {
-    if (smem > 48 * 1024)
-        CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    /* occupancy (and the opt-in for > 48 KB of dynamic shared memory) is queried once per kernel and size */
     int per_sm = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem));
-    if (per_sm < 1)
-        return fail(ctx, LUMACU_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    auto it = ctx->occupancy.find(fn);
+    if (it != ctx->occupancy.end() && it->second.first == smem) {
+        per_sm = it->second.second;
+    } else {
+        if (smem > 48 * 1024)
+            CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem));
+        if (per_sm < 1)
+            return fail(ctx, LUMACU_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+        ctx->occupancy[fn] = std::make_pair(smem, per_sm);
+    }
     uint32_t resident = (uint32_t)per_sm * (uint32_t)ctx->sm_count;
     uint32_t need = (ntiles + kThreads - 1) / kThreads;
     uint32_t g = resident;
     if (n_frames > 1) {
-        /* several frames per launch: spread the resident slots over the frames, but keep
-         * at least ~8 tiles per thread so that table staging stays amortised */
+        /* several frames per launch (grid.y = frame): blocks are scheduled frame-major, so the chip sweeps
+         * the batch roughly one frame at a time (few concurrent DRAM streams -- measured faster than
+         * spreading the resident slots over all frames at once), with >= ~8 tiles per thread so that the
+         * table staging stays amortised */
         uint32_t per_frame = (resident + n_frames - 1) / n_frames;
         uint32_t coarse = (need + 7) / 8;
         g = std::max(per_frame, std::min(coarse, resident));
@@ -700,7 +713,8 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     }
     enc_fn fn = nullptr;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
-    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic)
+    a.passthrough = ctx->passthrough ? 1 : 0;
+    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic && !ctx->passthrough)
         fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk);
     ctx->last_fast = fn != nullptr;
     if (!fn)
@@ -778,7 +792,8 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     dec_fn fn = nullptr;
     size_t smem = ctx->smem_dec;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
-    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic) {
+    a.passthrough = ctx->passthrough ? 1 : 0;
+    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !ctx->passthrough) {
         fn = pick_dec_fast(ctx->color_space, sub, bytes);
         smem = ctx->smem_dec_fast;
     }
@@ -977,6 +992,28 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
     CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LUMACU_OK;
+}
+
+extern "C" int lumacu_quantize_planes(lumacu_ctx *ctx, const float *frame, uint32_t w, uint32_t h, int profile,
+                                      uint8_t *const planes[3], const int32_t strides[3], lumacu_frame_stats *stats)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    ctx->passthrough = true;
+    const int rc = lumacu_encode(ctx, const_cast<float *>(frame), w, h, profile, 1.0f, planes, strides, 0, stats);
+    ctx->passthrough = false;
+    return rc;
+}
+
+extern "C" int lumacu_dequantize_planes(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
+                                        uint32_t w, uint32_t h, int profile, float *frame)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    ctx->passthrough = true;
+    const int rc = lumacu_decode(ctx, planes, strides, w, h, profile, 1.0f, frame);
+    ctx->passthrough = false;
+    return rc;
 }
 
 extern "C" int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs, float sc)
