@@ -225,6 +225,12 @@ int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, ui
 int lumacu_set_kernel_path(lumacu_ctx *ctx, int path);
 /* 1 if the last encode/decode launch on this context ran a tuned kernel, 0 if generic. */
 int lumacu_last_kernel_path(const lumacu_ctx *ctx);
+/* Tuning sweep (bench.py --sweep): pick one of the extra instantiations of the headline tuned kernels
+ * (variant = 10 * PF + MINB: PF 1 = next tile prefetched into registers, MINB = resident blocks per SM
+ * the register allocation is held to; 0 = the default) and optionally cap the resident blocks per SM
+ * of the persistent grid (0 = whatever the occupancy calculator allows).  Unknown variants fall back
+ * to the default.  All variants produce identical bits. */
+int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap);
 
 #ifdef __cplusplus
 }

@@ -25,10 +25,14 @@ LUMA_DECL_GENERIC(3)
 #undef LUMA_DECL_GENERIC
 
 /* tuned kernels (luma_fast.cuh); walk is the bucket walk length the search was planned with.
+ * variant = 10 * PF + MINB (see luma_kern_tu.cu); every configuration exists as variant 4, the headline
+ * configuration in a few more for the tuning sweep.
  * Return NULL when there is no instantiation for the request. */
+constexpr int kEncVariantPlain = 4, kDecVariantPlain = 4;
+constexpr unsigned kEncStagedSmemBytes = 6u * 512u * 8u; /* luma_fast.cuh kEncStageBlock */
 #define LUMA_DECL_FAST(CSV)                                          \
-    enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk);   \
-    dec_fn get_decode_fast_cs##CSV(bool sub, int bytes);
+    enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk, int variant); \
+    dec_fn get_decode_fast_cs##CSV(bool sub, int bytes, int variant);
 LUMA_DECL_FAST(0)
 LUMA_DECL_FAST(1)
 LUMA_DECL_FAST(2)

@@ -90,33 +90,78 @@ const void *quantize_kernel_ptr() { return (const void *)quantize_kernel; }
 
 #else /* LUMA_TU_FAST */
 
-template <bool SUB, int BYTES>
+/* Instantiations of the tuned kernels (see luma_fast.cuh).  variant = 10 * PF + MINB:
+ *   PF 0 = loads straight into registers, 1 = next tile prefetched into registers, 8 = next tile staged in
+ *   shared memory by a tensor-map (TMA) copy, 3..5 = timing diagnostics that skip part of the arithmetic;
+ *   MINB = resident blocks per SM the register allocation is held to.
+ * Every configuration exists as variant 4 (PF 0, the default); the headline instantiation (Lu'v', 4:2:0,
+ * 16-bit planes, walk 1) is additionally compiled in more variants so that scripts/sweep.py can re-measure
+ * the choice. */
+template <bool SUB, int BYTES, int PF>
 static enc_fn pick_walk(int walk)
 {
 #if LUMA_TU_CS == 0
     /* the headline colour space gets the exact walk length */
     if (walk <= 1)
-        return encode_fast_kernel<kCS, SUB, BYTES, 1>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 1, PF, 4>;
     if (walk == 2)
-        return encode_fast_kernel<kCS, SUB, BYTES, 2>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 2, PF, 4>;
 #endif
     if (walk <= 4)
-        return encode_fast_kernel<kCS, SUB, BYTES, 4>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 4, PF, 4>;
     return nullptr;
 }
 
-enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk)
+template <int PF>
+static enc_fn pick_enc_cfg(bool sub, int bytes, int walk)
 {
     if (sub)
-        return bytes == 2 ? pick_walk<true, 2>(walk) : pick_walk<true, 1>(walk);
-    return bytes == 2 ? pick_walk<false, 2>(walk) : pick_walk<false, 1>(walk);
+        return bytes == 2 ? pick_walk<true, 2, PF>(walk) : pick_walk<true, 1, PF>(walk);
+    return bytes == 2 ? pick_walk<false, 2, PF>(walk) : pick_walk<false, 1, PF>(walk);
 }
 
-dec_fn LUMA_CAT(get_decode_fast_cs, LUMA_TU_CS)(bool sub, int bytes)
+enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk, int variant)
 {
-    if (sub)
-        return bytes == 2 ? decode_fast_kernel<kCS, true, 2> : decode_fast_kernel<kCS, true, 1>;
-    return bytes == 2 ? decode_fast_kernel<kCS, false, 2> : decode_fast_kernel<kCS, false, 1>;
+    if (variant == 4)
+        return pick_enc_cfg<0>(sub, bytes, walk);
+#if LUMA_TU_CS == 0
+    if (sub && bytes == 2 && walk <= 1) {
+        switch (variant) {
+        case 2: return encode_fast_kernel<kCS, true, 2, 1, 0, 2>;
+        case 3: return encode_fast_kernel<kCS, true, 2, 1, 0, 3>;
+        case 12: return encode_fast_kernel<kCS, true, 2, 1, 1, 2>;
+        case 13: return encode_fast_kernel<kCS, true, 2, 1, 1, 3>;
+        case 84: return encode_fast_kernel<kCS, true, 2, 1, 8, 4>; /* tensor-map staging */
+        case 34: return encode_fast_kernel<kCS, true, 2, 1, 3, 4>; /* diagnostics: no colour, no search */
+        case 44: return encode_fast_kernel<kCS, true, 2, 1, 4, 4>; /* diagnostics: no search */
+        case 54: return encode_fast_kernel<kCS, true, 2, 1, 5, 4>; /* diagnostics: no colour */
+        default: break;
+        }
+    }
+#endif
+    return nullptr;
+}
+
+dec_fn LUMA_CAT(get_decode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int variant)
+{
+    if (variant == 4) {
+        if (sub)
+            return bytes == 2 ? decode_fast_kernel<kCS, true, 2, 0, 4> : decode_fast_kernel<kCS, true, 1, 0, 4>;
+        return bytes == 2 ? decode_fast_kernel<kCS, false, 2, 0, 4> : decode_fast_kernel<kCS, false, 1, 0, 4>;
+    }
+#if LUMA_TU_CS == 0
+    if (sub && bytes == 2) {
+        switch (variant) {
+        case 3: return decode_fast_kernel<kCS, true, 2, 0, 3>;
+        case 5: return decode_fast_kernel<kCS, true, 2, 0, 5>;
+        case 13: return decode_fast_kernel<kCS, true, 2, 1, 3>;
+        case 14: return decode_fast_kernel<kCS, true, 2, 1, 4>;
+        case 15: return decode_fast_kernel<kCS, true, 2, 1, 5>;
+        default: break;
+        }
+    }
+#endif
+    return nullptr;
 }
 
 #endif

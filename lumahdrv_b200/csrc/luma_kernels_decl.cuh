@@ -62,6 +62,9 @@ struct EncArgs {
     FrameStatsDev *stats;  /* [frames] */
     float2 nz;             /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
     int passthrough;       /* generic kernels: the frame is already colour-transformed (setChannels) */
+    /* tensor-map staged kernels: CUtensorMap over the frame batch, dims {w, h, 3 planes, frames} of f32,
+     * box {128, 2, 3, 1} (opaque 128 bytes so that this header does not need cuda.h) */
+    alignas(64) unsigned char rgb_tmap[128];
 };
 
 struct DecArgs {

@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cuda.h> /* CUtensorMap + enums only; the encoder entry point is resolved at run time */
+
 #include <algorithm>
 #include <string>
 #include <unordered_map>
@@ -79,6 +81,8 @@ struct lumacu_ctx {
     bool force_generic = false; /* tests: run the literal kernels */
     bool last_fast = false;     /* the last encode/decode launch used a tuned kernel */
     bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
+    int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
+    int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
 
     /* quantizer */
     bool configured = false;
@@ -569,6 +573,18 @@ extern "C" int lumacu_set_kernel_path(lumacu_ctx *ctx, int path)
 
 extern "C" int lumacu_last_kernel_path(const lumacu_ctx *ctx) { return (ctx && ctx->last_fast) ? 1 : 0; }
 
+extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (enc_variant < 0 || dec_variant < 0 || blocks_per_sm_cap < 0)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_tuning: negative argument");
+    ctx->enc_variant = enc_variant;
+    ctx->dec_variant = dec_variant;
+    ctx->grid_cap = blocks_per_sm_cap;
+    return LUMACU_OK;
+}
+
 /* ================================ launches ============================================ */
 namespace {
 
@@ -590,24 +606,62 @@ dec_fn pick_dec(int cs, bool sub, int bytes, bool vec)
     default: return get_decode_generic_cs3(sub, bytes, vec);
     }
 }
-enc_fn pick_enc_fast(int cs, bool sub, int bytes, int walk)
+enc_fn pick_enc_fast(int cs, bool sub, int bytes, int walk, int variant)
 {
     switch (cs) {
-    case CS_LUV: return get_encode_fast_cs0(sub, bytes, walk);
-    case CS_RGB: return get_encode_fast_cs1(sub, bytes, walk);
-    case CS_YCBCR: return get_encode_fast_cs2(sub, bytes, walk);
-    default: return get_encode_fast_cs3(sub, bytes, walk);
+    case CS_LUV: return get_encode_fast_cs0(sub, bytes, walk, variant);
+    case CS_RGB: return get_encode_fast_cs1(sub, bytes, walk, variant);
+    case CS_YCBCR: return get_encode_fast_cs2(sub, bytes, walk, variant);
+    default: return get_encode_fast_cs3(sub, bytes, walk, variant);
     }
 }
-dec_fn pick_dec_fast(int cs, bool sub, int bytes)
+dec_fn pick_dec_fast(int cs, bool sub, int bytes, int variant)
 {
     switch (cs) {
-    case CS_LUV: return get_decode_fast_cs0(sub, bytes);
-    case CS_RGB: return get_decode_fast_cs1(sub, bytes);
-    case CS_YCBCR: return get_decode_fast_cs2(sub, bytes);
-    default: return get_decode_fast_cs3(sub, bytes);
+    case CS_LUV: return get_decode_fast_cs0(sub, bytes, variant);
+    case CS_RGB: return get_decode_fast_cs1(sub, bytes, variant);
+    case CS_YCBCR: return get_decode_fast_cs2(sub, bytes, variant);
+    default: return get_decode_fast_cs3(sub, bytes, variant);
     }
 }
+
+/* CUtensorMap over a batch of planar f32 frames for the tensor-map staged encode kernel: dims (fastest first)
+ * {w, h, 3 planes, n_frames}, box {128, 2, 3, 1} -- one copy brings the 128-pixel x 2-row x 3-plane footprint
+ * of a warp's 32 tiles.  cuTensorMapEncodeTiled is resolved through the runtime so libcuda is not linked. */
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_rgb_tensor_map(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_t h, size_t plane_stride, size_t frame_stride,
+                        uint32_t n_frames, unsigned char out[128])
+{
+    static encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp) {
+            (void)cudaGetLastError();
+            return fail(ctx, LUMACU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+        }
+        encode = (encode_tiled_fn)fp;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t dims[4] = {w, h, 3, n_frames};
+    const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)plane_stride * 4, (cuuint64_t)frame_stride * 4};
+    const cuuint32_t box[4] = {128, 2, 3, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)d_rgb, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(ctx, LUMACU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    memcpy(out, &tm, 128);
+    return LUMACU_OK;
+}
+
+/* Default variants of the tuned kernels, from the sweep on B200 (DESIGN.md "kernel tuning"). */
+constexpr int kEncDefaultVariant = kEncVariantPlain;
+constexpr int kDecDefaultVariant = kDecVariantPlain;
 
 inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
@@ -627,6 +681,8 @@ int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint
             return fail(ctx, LUMACU_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
         ctx->occupancy[fn] = std::make_pair(smem, per_sm);
     }
+    if (ctx->grid_cap > 0)
+        per_sm = std::min(per_sm, ctx->grid_cap);
     uint32_t resident = (uint32_t)per_sm * (uint32_t)ctx->sm_count;
     uint32_t need = (ntiles + kThreads - 1) / kThreads;
     uint32_t g = resident;
@@ -714,14 +770,30 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     enc_fn fn = nullptr;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
     a.passthrough = ctx->passthrough ? 1 : 0;
-    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic && !ctx->passthrough)
-        fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk);
+    size_t smem = ctx->smem_enc;
+    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic && !ctx->passthrough) {
+        int variant = ctx->enc_variant ? ctx->enc_variant : kEncDefaultVariant;
+        const int pf = variant / 10;
+        const bool staged = (pf == 8);
+        if (staged && (w % 128u) != 0) /* tensor-map staging: a warp must not straddle image rows */
+            variant = kEncVariantPlain;
+        if (variant / 10 == 8 &&
+            make_rgb_tensor_map(ctx, d_rgb, w, h, a.rgb_plane_stride, a.rgb_frame_stride, n_frames, a.rgb_tmap) != LUMACU_OK)
+            variant = kEncVariantPlain;
+        fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk, variant);
+        if (!fn && variant != kEncVariantPlain) {
+            variant = kEncVariantPlain;
+            fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk, variant);
+        }
+        if (fn && staged && variant != kEncVariantPlain)
+            smem += kEncStagedSmemBytes;
+    }
     ctx->last_fast = fn != nullptr;
     if (!fn)
         fn = pick_enc(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
     uint32_t gx = 1;
-    rc = grid_for(ctx, (const void *)fn, ctx->smem_enc, ntiles, n_frames, &gx);
+    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, &gx);
     if (rc)
         return rc;
     if (d_stats) {
@@ -738,7 +810,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
         a.counter = (uint32_t *)ctx->d_counter.p;
         a.stats = (FrameStatsDev *)d_stats;
     }
-    fn<<<dim3(gx, n_frames), kThreads, ctx->smem_enc, st>>>(a);
+    fn<<<dim3(gx, n_frames), kThreads, smem, st>>>(a);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -794,7 +866,9 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
     a.passthrough = ctx->passthrough ? 1 : 0;
     if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !ctx->passthrough) {
-        fn = pick_dec_fast(ctx->color_space, sub, bytes);
+        fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
+        if (!fn)
+            fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
         smem = ctx->smem_dec_fast;
     }
     ctx->last_fast = fn != nullptr;
