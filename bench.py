@@ -38,10 +38,10 @@ WORKLOAD = "4K (3840x2160) f32 RGB, PQ, Lu'v' 11/8-bit, profile 2 (4:2:0 LE16): 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=4, help="frames per GPU per end-to-end step")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames per worker in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -109,7 +109,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -278,14 +278,65 @@ def ours_arm(args):
         dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=L.CS_LUV, ptfBitDepth=QUANT["ptfBitDepth"],
                                           colorBitDepth=QUANT["colorBitDepth"], profile=QUANT["profile"]))
         dec.initialize()
+        # one band per call: with the encoder and the decoder running concurrently the PCIe link is already busy in
+        # both directions, and banding only adds API calls (measured: 2.80 ms per frame pair at 1 band, 3.62 at 8;
+        # a lone encoder or decoder is fastest at 8 bands: 1.96 / 2.05 ms vs 2.33 / 2.28 -- scripts/e2e_probe.py)
+        for obj in (enc, dec):
+            L._lib.check(obj.m_quant._lib.lumacu_set_host_bands(obj.m_quant.ctx.handle, 1), obj.m_quant.ctx.handle, "bands")
         dec.m_frame = h_out.numpy()
         np_in = h_in.numpy()
         np_planes = [p.numpy() for p in h_planes]
 
+        # Two host threads, like the two programs of the reference (lumaenc | lumadec): the encoder thread runs
+        # LumaEncoder.encode on frame i+1 while the decoder thread runs LumaDecoder.decode on the planes of
+        # frame i (each object has its own context and streams; ctypes releases the GIL inside the C call), so
+        # both PCIe directions are busy.  Planes travel GPU -> host -> GPU like they would through VP9.
+        import queue
+        slots = [[p.clone().pin_memory().numpy() for p in h_planes] for _ in range(2)]  # double-buffered host planes
+        h_outs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+        free_q, full_q = queue.Queue(), queue.Queue()
+        errors = []
+
+        def enc_thread(nframes):
+            try:
+                for i in range(nframes):
+                    s = free_q.get()
+                    enc.encode(np_in[i % Fe], slots[s])       # H2D 12 B/px, kernel, D2H 3 B/px
+                    full_q.put(s)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+            full_q.put(None)
+
+        def dec_thread():
+            try:
+                k = 0
+                while True:
+                    s = full_q.get()
+                    if s is None:
+                        return
+                    dec.m_frame = h_outs[k & 1]
+                    dec.decode(slots[s], W, H)                # H2D 3 B/px, kernel, D2H 12 B/px
+                    free_q.put(s)
+                    k += 1
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        def e2e_run(nframes):
+            while not free_q.empty():
+                free_q.get()
+            free_q.put(0)
+            free_q.put(1)
+            te = threading.Thread(target=enc_thread, args=(nframes,))
+            td = threading.Thread(target=dec_thread)
+            te.start()
+            td.start()
+            te.join()
+            td.join()
+            if errors:
+                raise errors[0]
+
         def e2e_step():
-            for i in range(Fe):
-                enc.encode(np_in[i], np_planes)      # H2D 12 B/px, kernel, D2H 3 B/px
-                dec.decode(np_planes, W, H)          # H2D 3 B/px, kernel, D2H 12 B/px
+            e2e_run(Fe)
 
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -294,11 +345,13 @@ def ours_arm(args):
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_run(Fe * e2e_steps)   # K steps back to back, the pipeline stays full across step boundaries
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e_launches = enc.m_quant.ctx.launch_count + dec.m_quant.ctx.launch_count - l0
+        # the last decoded frame must be the round trip of its input (spot check, outside the timed region)
+        chk = t.decode(t.encode(rgb[(Fe * e2e_steps - 1) % Fe][None]), W, H)[0].cpu().numpy()
+        assert np.array_equal(chk.view(np.uint32), h_outs[(Fe * e2e_steps - 1) & 1].view(np.uint32)), "e2e result differs"
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -307,7 +360,8 @@ def ours_arm(args):
         e2e = {"value": world * Fe * W * H * e2e_steps / dt / 1e6, "unit": "Mpixels/s",
                "h2d_bytes_per_step": Fe * (12 * W * H + plane_bytes), "d2h_bytes_per_step": Fe * (12 * W * H + plane_bytes),
                "steps": e2e_steps, "frames_per_step": Fe, "gpu_launches": e2e_launches,
-               "api": "lumacu_encode + lumacu_decode (host pointers, pinned), via LumaEncoder.encode / LumaDecoder.decode"}
+               "api": "LumaEncoder.encode / LumaDecoder.decode -> lumacu_encode + lumacu_decode (host pointers, pinned), "
+                      "encoder and decoder objects on two host threads (frame i+1 encodes while frame i decodes)"}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

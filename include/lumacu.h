@@ -110,6 +110,10 @@ void *lumacu_stream(lumacu_ctx *ctx);
  * full PCIe rate).  Not tied to a context. */
 int lumacu_host_alloc(size_t bytes, void **out);
 int lumacu_host_free(void *p);
+/* Page-lock memory the caller already owns (e.g. the vpx_image_t planes libvpx allocated,
+ * src/luma_encoder.cpp:121-128) so that copies to/from it are direct DMA.  Registering twice is OK. */
+int lumacu_host_register(void *p, size_t bytes);
+int lumacu_host_unregister(void *p);
 
 /* ---- quantizer -------------------------------------------------------------- */
 /* Host-side LUT construction = the table half of LumaQuantizer::setQuantizer
@@ -225,7 +229,10 @@ int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, ui
 int lumacu_set_kernel_path(lumacu_ctx *ctx, int path);
 /* 1 if the last encode/decode launch on this context ran a tuned kernel, 0 if generic. */
 int lumacu_last_kernel_path(const lumacu_ctx *ctx);
-/* Tuning sweep (bench.py --sweep): pick one of the extra instantiations of the headline tuned kernels
+/* Host-pointer entry points cut a frame into row bands whose H2D copy, kernel and D2H copy overlap on three
+ * streams (DESIGN.md "host staging").  0 = automatic (8 bands for frames >= 1 Mpixel, else 1). */
+int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
+/* Tuning sweep: pick one of the extra instantiations of the headline tuned kernels
  * (variant = 10 * PF + MINB: PF 1 = next tile prefetched into registers, MINB = resident blocks per SM
  * the register allocation is held to; 0 = the default) and optionally cap the resident blocks per SM
  * of the persistent grid (0 = whatever the occupancy calculator allows).  Unknown variants fall back

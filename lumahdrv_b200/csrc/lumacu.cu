@@ -97,8 +97,12 @@ struct lumacu_ctx {
     /* stats workspace */
     DeviceBuffer d_partial, d_counter;
 
-    /* staging for the host-pointer entry points */
+    /* staging for the host-pointer entry points: row bands flow H2D (s_in) -> kernel (stream) -> D2H (s_out) */
     DeviceBuffer d_rgb, d_planes, d_stats, d_aux;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
+    size_t plane_stride_override = 0; /* floats between the R,G,B planes of the NEXT *_dev launch (0 = w*h): band launches */
+    int host_bands = 0;               /* tuning: number of row bands per host-pointer call (0 = automatic) */
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
 };
@@ -372,6 +376,11 @@ extern "C" int lumacu_create(int device, lumacu_ctx **out)
                     device, prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess) {
+        lumacu_destroy(ctx);
+        return fail(nullptr, LUMACU_ERR_CUDA, "lumacu_create: %s", cudaGetErrorString(e));
+    }
     *out = ctx;
     return LUMACU_OK;
 }
@@ -388,6 +397,14 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
             cudaFree(b->p);
     if (ctx->h_pin)
         cudaFreeHost(ctx->h_pin);
+    for (cudaEvent_t ev : ctx->ev_in)
+        cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_k)
+        cudaEventDestroy(ev);
+    if (ctx->s_in)
+        cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out)
+        cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LUMACU_OK;
@@ -407,6 +424,31 @@ extern "C" int lumacu_synchronize(lumacu_ctx *ctx)
 }
 
 extern "C" void *lumacu_stream(lumacu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int lumacu_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return LUMACU_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, LUMACU_ERR_CUDA, "cudaHostRegister(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_host_unregister(void *p)
+{
+    if (!p)
+        return LUMACU_OK;
+    if (cudaHostUnregister(p) != cudaSuccess)
+        cudaGetLastError();
+    return LUMACU_OK;
+}
 
 extern "C" int lumacu_host_alloc(size_t bytes, void **out)
 {
@@ -572,6 +614,16 @@ extern "C" int lumacu_set_kernel_path(lumacu_ctx *ctx, int path)
 }
 
 extern "C" int lumacu_last_kernel_path(const lumacu_ctx *ctx) { return (ctx && ctx->last_fast) ? 1 : 0; }
+
+extern "C" int lumacu_set_host_bands(lumacu_ctx *ctx, int bands)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (bands < 0 || bands > 64)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_host_bands: %d not in [0, 64]", bands);
+    ctx->host_bands = bands;
+    return LUMACU_OK;
+}
 
 extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap)
 {
@@ -749,7 +801,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     a.q = ctx->q;
     a.rgb = d_rgb;
     a.rgb_out = d_rgb_out;
-    a.rgb_plane_stride = (size_t)w * h;
+    a.rgb_plane_stride = ctx->plane_stride_override ? ctx->plane_stride_override : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
     a.out_plane_stride = a.rgb_plane_stride;
     a.out_frame_stride = a.rgb_frame_stride;
@@ -846,7 +898,7 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     DecArgs a{};
     a.q = ctx->q;
     a.rgb = d_rgb;
-    a.rgb_plane_stride = (size_t)w * h;
+    a.rgb_plane_stride = ctx->plane_stride_override ? ctx->plane_stride_override : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
     a.w = w;
     a.h = h;
@@ -983,6 +1035,43 @@ void device_plane_layout(uint32_t w, uint32_t h, int profile, int32_t dstride[3]
 
 } // namespace
 
+namespace {
+
+/* Row bands for the host-pointer entry points.  A frame is cut into nb horizontal bands on even-row
+ * boundaries (2x2 chroma blocks stay intact); band b's H2D copy, kernel and D2H copy run on three streams
+ * chained by events, so the copy of band b+1 overlaps the kernel of band b and the read-back of band b-1:
+ * the call costs about max(H2D, D2H) instead of H2D + kernel + D2H.  Small frames use one band. */
+int band_count(const lumacu_ctx *ctx, uint32_t w, uint32_t h)
+{
+    if (ctx->host_bands > 0)
+        return std::max(1, std::min<int>(ctx->host_bands, (int)(h / 2)));
+    const size_t px = (size_t)w * h;
+    if (px < (size_t)1 << 20)
+        return 1;
+    return (int)std::min<size_t>(8, h / 64);
+}
+
+int ensure_events(lumacu_ctx *ctx, int nb)
+{
+    while ((int)ctx->ev_in.size() < nb) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CU_TRY(ctx, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ctx->ev_in.push_back(a);
+        CU_TRY(ctx, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ctx->ev_k.push_back(b);
+    }
+    return LUMACU_OK;
+}
+
+inline uint32_t band_row(uint32_t h, int nb, int b) /* first row of band b; even; band nb starts at h */
+{
+    if (b >= nb)
+        return h;
+    return (uint32_t)(((uint64_t)(h / 2) * b / nb) * 2);
+}
+
+} // namespace
+
 extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
                              uint8_t *const planes[3], const int32_t strides[3], int write_back,
                              lumacu_frame_stats *stats)
@@ -1001,31 +1090,60 @@ extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
     const int bytes = profile > 1 ? 2 : 1;
+    const bool sub = (profile == 0 || profile == 2);
     for (int p = 0; p < 3; p++)
         if (strides[p] < (int32_t)(pw[p] * bytes))
             return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode: stride[%d] smaller than a row", p);
     int32_t dstride[3];
     size_t off[3], ptotal;
     device_plane_layout(w, h, profile, dstride, off, &ptotal);
+    const int nb = band_count(ctx, w, h);
     if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) ||
-        (rc = reserve(ctx, ctx->d_stats, sizeof(lumacu_frame_stats))))
+        (rc = reserve(ctx, ctx->d_stats, sizeof(lumacu_frame_stats) * 64)) || (rc = ensure_events(ctx, nb)))
         return rc;
     float *d_rgb = (float *)ctx->d_rgb.p;
     uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
                       (uint8_t *)ctx->d_planes.p + off[2]};
-    CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, npx * 12, cudaMemcpyHostToDevice, ctx->stream));
-    rc = lumacu_encode_dev(ctx, d_rgb, write_back ? d_rgb : nullptr, w, h, profile, pre_scaling, dp, dstride, 1, 0, nullptr,
-                           stats ? (lumacu_frame_stats *)ctx->d_stats.p : nullptr, ctx->stream);
-    if (rc)
-        return rc;
-    for (int p = 0; p < 3; p++)
-        CU_TRY(ctx, cudaMemcpy2DAsync(planes[p], (size_t)strides[p], dp[p], (size_t)dstride[p], (size_t)pw[p] * bytes, ph[p],
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-    if (write_back)
-        CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    lumacu_frame_stats *d_stats = (lumacu_frame_stats *)ctx->d_stats.p;
+    for (int b = 0; b < nb; b++) {
+        const uint32_t y0 = band_row(h, nb, b), y1 = band_row(h, nb, b + 1), rows = y1 - y0;
+        /* the band's rows of the three planes in one strided copy (pitch = one plane) */
+        CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb + (size_t)y0 * w, npx * 4, rgb + (size_t)y0 * w, npx * 4, (size_t)rows * w * 4, 3,
+                                      cudaMemcpyHostToDevice, ctx->s_in));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        const uint32_t cy0 = sub ? y0 >> 1 : y0;
+        uint8_t *bp[3] = {dp[0] + (size_t)y0 * dstride[0], dp[1] + (size_t)cy0 * dstride[1], dp[2] + (size_t)cy0 * dstride[2]};
+        float *band = d_rgb + (size_t)y0 * w;
+        ctx->plane_stride_override = npx;
+        rc = lumacu_encode_dev(ctx, band, write_back ? band : nullptr, w, rows, profile, pre_scaling, bp, dstride, 1, 0, nullptr,
+                               stats ? d_stats + b : nullptr, ctx->stream);
+        ctx->plane_stride_override = 0;
+        if (rc)
+            return rc;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
+        for (int p = 0; p < 3; p++) {
+            const uint32_t py0 = (p && sub) ? y0 >> 1 : y0, prows = (p && sub) ? rows >> 1 : rows;
+            CU_TRY(ctx, cudaMemcpy2DAsync(planes[p] + (size_t)py0 * strides[p], (size_t)strides[p], dp[p] + (size_t)py0 * dstride[p],
+                                          (size_t)dstride[p], (size_t)pw[p] * bytes, prows, cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        if (write_back)
+            CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3,
+                                          cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    lumacu_frame_stats hs[64];
     if (stats)
-        CU_TRY(ctx, cudaMemcpyAsync(stats, ctx->d_stats.p, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(hs, d_stats, sizeof(lumacu_frame_stats) * nb, cudaMemcpyDeviceToHost, ctx->s_out));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
+    if (stats) {
+        *stats = hs[0];
+        for (int b = 1; b < nb; b++) {
+            stats->sum += hs[b].sum;
+            stats->max = fmaxf(stats->max, hs[b].max);
+            stats->min = fminf(stats->min, hs[b].min);
+        }
+    }
     return LUMACU_OK;
 }
 
@@ -1046,25 +1164,43 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
     const int bytes = profile > 1 ? 2 : 1;
+    const bool sub = (profile == 0 || profile == 2);
     for (int p = 0; p < 3; p++)
         if (strides[p] < (int32_t)(pw[p] * bytes))
             return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode: stride[%d] smaller than a row", p);
     int32_t dstride[3];
     size_t off[3], ptotal;
     device_plane_layout(w, h, profile, dstride, off, &ptotal);
-    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)))
+    /* the reference accepts odd decoded sizes in principle (plane dims are rounded up); bands need even rows */
+    const int nb = (h % 2 == 0) ? band_count(ctx, w, h) : 1;
+    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) || (rc = ensure_events(ctx, nb)))
         return rc;
     float *d_rgb = (float *)ctx->d_rgb.p;
-    const uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
-                            (uint8_t *)ctx->d_planes.p + off[2]};
-    for (int p = 0; p < 3; p++)
-        CU_TRY(ctx, cudaMemcpy2DAsync((void *)dp[p], (size_t)dstride[p], planes[p], (size_t)strides[p], (size_t)pw[p] * bytes,
-                                      ph[p], cudaMemcpyHostToDevice, ctx->stream));
-    rc = lumacu_decode_dev(ctx, dp, dstride, w, h, profile, pre_scaling, d_rgb, 1, 0, nullptr, ctx->stream);
-    if (rc)
-        return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
+                      (uint8_t *)ctx->d_planes.p + off[2]};
+    for (int b = 0; b < nb; b++) {
+        const uint32_t y0 = nb == 1 ? 0 : band_row(h, nb, b), y1 = nb == 1 ? h : band_row(h, nb, b + 1), rows = y1 - y0;
+        const uint8_t *bp[3];
+        for (int p = 0; p < 3; p++) {
+            const uint32_t py0 = (p && sub) ? y0 >> 1 : y0, prows = (p && sub) ? (rows + 1) >> 1 : rows;
+            CU_TRY(ctx, cudaMemcpy2DAsync(dp[p] + (size_t)py0 * dstride[p], (size_t)dstride[p], planes[p] + (size_t)py0 * strides[p],
+                                          (size_t)strides[p], (size_t)pw[p] * bytes, prows, cudaMemcpyHostToDevice, ctx->s_in));
+            bp[p] = dp[p] + (size_t)py0 * dstride[p];
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        float *band = d_rgb + (size_t)y0 * w;
+        ctx->plane_stride_override = npx;
+        rc = lumacu_decode_dev(ctx, bp, dstride, w, rows, profile, pre_scaling, band, 1, 0, nullptr, ctx->stream);
+        ctx->plane_stride_override = 0;
+        if (rc)
+            return rc;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
+        CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3, cudaMemcpyDeviceToHost,
+                                      ctx->s_out));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
     return LUMACU_OK;
 }
 

@@ -18,6 +18,8 @@
 
 #include "luma_frame.h"
 #include "luma_quantizer.h"
+
+#include <vector>
 #include "mkv_interface.h"
 
 #include "vp8dx.h"
@@ -91,10 +93,13 @@ public:
     void setParams(LumaDecoderParams params) { m_params = params; }
 
 private:
+    void registerPlanes();
+
     vpx_codec_ctx_t m_codec;
     vpx_image_t *m_vpxFrame;
     LumaDecoderParams m_params;
     bool m_firstFrame, m_haveCodec;
+    std::vector<unsigned char *> m_registered; /* page-locked libvpx frame buffers */
 };
 
 #endif // LUMA_DECODER_H

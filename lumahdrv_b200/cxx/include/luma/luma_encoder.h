@@ -111,6 +111,7 @@ private:
     LumaEncoderParams m_params;
     bool m_strict, m_haveImage, m_haveCodec;
     double m_lastMean;
+    void *m_registered; /* page-locked range of m_rawFrame (lumacu_host_register) */
 };
 
 #endif // LUMA_ENCODER_H

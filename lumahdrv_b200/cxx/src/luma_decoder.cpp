@@ -15,6 +15,7 @@
 #include "luma_exception.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -44,8 +45,27 @@ LumaDecoder::LumaDecoder(const char *inputFile, bool verbose)
         initialize(inputFile, verbose);
 }
 
+/* libvpx hands out frames from a small pool of buffers it owns; page-lock each buffer the first time it is seen
+ * (direct DMA instead of a staged copy).  LUMA_NO_REGISTER_VPX=1 disables it. */
+void LumaDecoder::registerPlanes()
+{
+    static const bool off = getenv("LUMA_NO_REGISTER_VPX") && getenv("LUMA_NO_REGISTER_VPX")[0] != '0';
+    if (off || !m_vpxFrame || !m_vpxFrame->planes[0] || !m_vpxFrame->planes[2] || m_registered.size() >= 32)
+        return;
+    unsigned char *lo = m_vpxFrame->planes[0];
+    const unsigned chromaRows = m_vpxFrame->y_chroma_shift ? (m_vpxFrame->d_h + 1) >> 1 : m_vpxFrame->d_h;
+    unsigned char *hi = m_vpxFrame->planes[2] + (size_t)m_vpxFrame->stride[2] * chromaRows;
+    for (size_t i = 0; i < m_registered.size(); i++)
+        if (m_registered[i] == lo)
+            return;
+    if (hi > lo && lumacu_host_register(lo, (size_t)(hi - lo)) == 0)
+        m_registered.push_back(lo);
+}
+
 LumaDecoder::~LumaDecoder()
 {
+    for (size_t i = 0; i < m_registered.size(); i++)
+        lumacu_host_unregister(m_registered[i]);
     if (m_haveCodec && vpx_codec_destroy(&m_codec))
         fprintf(stderr, "Failed to destroy vpx codec\n");
 }
@@ -167,6 +187,7 @@ LumaFrame *LumaDecoder::decode()
     }
     lumacu_ctx *ctx = m_quant.device();
     const int32_t strides[3] = {m_vpxFrame->stride[0], m_vpxFrame->stride[1], m_vpxFrame->stride[2]};
+    registerPlanes();
     const int hi = (m_vpxFrame->fmt & VPX_IMG_FMT_HIGHBITDEPTH) ? 2 : 0;
     const int profile = hi + (m_vpxFrame->x_chroma_shift ? 0 : 1);
     const int rc = lumacu_decode(ctx, m_vpxFrame->planes, strides, m_frame.width, m_frame.height, profile,

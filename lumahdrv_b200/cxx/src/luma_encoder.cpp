@@ -49,7 +49,7 @@ bool env_flag(const char *name)
 
 LumaEncoder::LumaEncoder()
     : m_frameCount(0), m_strict(env_flag("LUMA_STRICT_SIDE_EFFECT")), m_haveImage(false), m_haveCodec(false),
-      m_lastMean(0.0)
+      m_lastMean(0.0), m_registered(NULL)
 {
     memset(&m_codec, 0, sizeof(m_codec));
     memset(&m_rawFrame, 0, sizeof(m_rawFrame));
@@ -57,6 +57,8 @@ LumaEncoder::LumaEncoder()
 
 LumaEncoder::~LumaEncoder()
 {
+    if (m_registered)
+        lumacu_host_unregister(m_registered);
     if (m_haveImage)
         vpx_img_free(&m_rawFrame);
     if (m_haveCodec && vpx_codec_destroy(&m_codec))
@@ -106,6 +108,13 @@ bool LumaEncoder::initialize(const char *outputFile, const unsigned int w, const
     if (!vpx_img_alloc(&m_rawFrame, kFormats[p.profile].fmt, w, h, 32))
         throw LumaException(kFormats[p.profile].err);
     m_haveImage = true;
+    /* page-lock the image libvpx allocated so the planes come back from the GPU by direct DMA */
+    if (!env_flag("LUMA_NO_REGISTER_VPX") && m_rawFrame.planes[0] && m_rawFrame.planes[2]) {
+        const unsigned chromaRows = (p.profile % 2 == 0) ? (h + 1) / 2 : h;
+        unsigned char *end = m_rawFrame.planes[2] + (size_t)m_rawFrame.stride[2] * chromaRows;
+        if (end > m_rawFrame.planes[0] && lumacu_host_register(m_rawFrame.planes[0], (size_t)(end - m_rawFrame.planes[0])) == 0)
+            m_registered = m_rawFrame.planes[0];
+    }
 
     const vpx_codec_iface_t *iface = vpx_codec_vp9_cx();
     vpx_codec_enc_cfg_t cfg;

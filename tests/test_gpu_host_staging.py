@@ -1,0 +1,111 @@
+"""GPU (-m gpu): the host-pointer entry points (lumacu_encode / lumacu_decode) cut frames into row bands that
+overlap H2D copy, kernel and D2H copy on three streams.  Whatever the band count, the
+planes, the decoded floats and the frame statistics must equal the single-band result and the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _set_bands(L, obj, n):
+    from lumahdrv_b200._lib import check
+    hnd = obj.m_quant.ctx.handle
+    check(obj.m_quant._lib.lumacu_set_host_bands(hnd, n), hnd, "lumacu_set_host_bands")
+
+
+@pytest.mark.parametrize("w,h,profile,cs", [(1920, 1080, 2, "LUV"), (1280, 722, 3, "LUV"), (1026, 1030, 0, "YCBCR"),
+                                            (2048, 1024, 2, "XYZ")])
+def test_banded_equals_single_band_and_oracle(lumalib, po, w, h, profile, cs):
+    L = lumalib
+    cbits = 10 if cs == "YCBCR" else 8
+    bits = 8 if profile < 2 else 11
+    enc = L.LumaEncoder()
+    enc.setParams(L.LumaEncoderParams(ptf="PQ", ptfBitDepth=bits, colorSpace=cs, colorBitDepth=min(cbits, 8 if profile < 2 else 12),
+                                      profile=profile, bitDepth=8 if profile < 2 else 12))
+    enc.initialize(None, w, h)
+    cb = enc.getParams().colorBitDepth
+    dec = L.LumaDecoder()
+    dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=enc.getParams().colorSpace, ptfBitDepth=bits, colorBitDepth=cb,
+                                      profile=profile))
+    dec.initialize()
+    o = po.Oracle().setQuantizer("PQ", bits, cs, cb)
+    frame = po.noise_frame(w, h, seed=99)
+    frame[:, 5, 7] = np.nan
+    frame[0, h - 1, w - 1] = -3.0
+    ref_planes, ref_avg = o.encode(frame.copy(), profile, 1.0)
+    ref_out = o.decode(ref_planes, w, h, profile, 1.0)
+    nbytes = 2 if profile > 1 else 1
+    results = []
+    for bands in (1, 3, 8, 0):
+        _set_bands(L, enc, bands)
+        _set_bands(L, dec, bands)
+        planes = enc.encode(frame.copy(), L.alloc_planes(w, h, profile))
+        for p, (a, b, (pw, ph)) in enumerate(zip(planes, ref_planes, po.plane_dims(w, h, profile))):
+            assert np.array_equal(a[:ph, :pw * nbytes], b[:ph, :pw * nbytes]), f"bands={bands}: plane {p} differs from the oracle"
+        out = dec.decode(planes, w, h).copy()
+        assert bits_equal(out, ref_out), f"bands={bands}: decoded floats differ from the oracle"
+        results.append(enc.last_stats)
+    # statistics: NaN pixel is ignored by max/min, poisons nothing else; band sums add up
+    for st in results[1:]:
+        assert st["max"] == results[0]["max"] and st["min"] == results[0]["min"]
+        if np.isfinite(results[0]["sum"]):
+            assert abs(st["sum"] - results[0]["sum"]) <= 1e-9 * abs(results[0]["sum"])
+
+
+def test_encoder_and_decoder_objects_run_concurrently_on_two_threads(lumalib, po):
+    """bench.py's end-to-end arm: encode(i+1) on one thread while decode(i) runs on another."""
+    L = lumalib
+    w, h, n = 1920, 1080, 6
+    enc = L.LumaEncoder()
+    enc.initialize(None, w, h)
+    dec = L.LumaDecoder()
+    dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=L.CS_LUV))
+    dec.initialize()
+    o = po.Oracle().setQuantizer("PQ", 11, "LUV", 8)
+    frames = [po.noise_frame(w, h, seed=1000 + i) for i in range(n)]
+    planes = [L.alloc_planes(w, h, 2) for _ in range(n)]
+    outs = [None] * n
+    done = [threading.Event() for _ in range(n)]
+    errors = []
+
+    def encoder():
+        try:
+            for i in range(n):
+                enc.encode(frames[i], planes[i])
+                done[i].set()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            for d in done:
+                d.set()
+
+    def decoder():
+        try:
+            for i in range(n):
+                done[i].wait()
+                outs[i] = dec.decode(planes[i], w, h).copy()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=encoder), threading.Thread(target=decoder)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    for i in range(n):
+        ref_planes, _ = o.encode(frames[i].copy(), 2, 1.0)
+        for a, b, (pw, ph) in zip(planes[i], ref_planes, po.plane_dims(w, h, 2)):
+            assert np.array_equal(a[:ph, :pw * 2], b[:ph, :pw * 2])
+        assert bits_equal(outs[i], o.decode(ref_planes, w, h, 2, 1.0))
+
+
+def test_host_register_roundtrip(lumalib):
+    import ctypes as C
+
+    lib = lumalib.lib()
+    buf = np.zeros(1 << 20, dtype=np.uint8)
+    assert lib.lumacu_host_register(C.c_void_p(buf.ctypes.data), buf.nbytes) == 0
+    assert lib.lumacu_host_register(C.c_void_p(buf.ctypes.data), buf.nbytes) == 0  # twice is fine
+    assert lib.lumacu_host_unregister(C.c_void_p(buf.ctypes.data)) == 0
