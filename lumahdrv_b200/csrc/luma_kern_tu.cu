@@ -100,6 +100,13 @@ const void *quantize_kernel_ptr() { return (const void *)quantize_kernel; }
 template <bool SUB, int BYTES, int PF>
 static enc_fn pick_walk(int walk)
 {
+#if LUMA_TU_CS == 0 || LUMA_TU_CS == 3
+    if (walk == 0) /* direct search table (values clamped to [1e-4, 1e8]: Lu'v' Y, XYZ) */
+        return encode_fast_kernel<kCS, SUB, BYTES, 0, PF, 4>;
+#else
+    if (walk == 0)
+        return nullptr;
+#endif
 #if LUMA_TU_CS == 0
     /* the headline colour space gets the exact walk length */
     if (walk <= 1)
@@ -125,16 +132,23 @@ enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk, i
     if (variant == 4)
         return pick_enc_cfg<0>(sub, bytes, walk);
 #if LUMA_TU_CS == 0
-    if (sub && bytes == 2 && walk <= 1) {
+    if (sub && bytes == 2 && walk == 0) {
+        switch (variant) {
+        case 3: return encode_fast_kernel<kCS, true, 2, 0, 0, 3>;
+        case 5: return encode_fast_kernel<kCS, true, 2, 0, 0, 5>;
+        case 84: return encode_fast_kernel<kCS, true, 2, 0, 8, 4>; /* tensor-map staging */
+        case 34: return encode_fast_kernel<kCS, true, 2, 0, 3, 4>; /* diagnostics: no colour, no search */
+        case 44: return encode_fast_kernel<kCS, true, 2, 0, 4, 4>; /* diagnostics: no search */
+        case 54: return encode_fast_kernel<kCS, true, 2, 0, 5, 4>; /* diagnostics: no colour */
+        default: break;
+        }
+    }
+    if (sub && bytes == 2 && walk == 1) {
         switch (variant) {
         case 2: return encode_fast_kernel<kCS, true, 2, 1, 0, 2>;
         case 3: return encode_fast_kernel<kCS, true, 2, 1, 0, 3>;
         case 12: return encode_fast_kernel<kCS, true, 2, 1, 1, 2>;
         case 13: return encode_fast_kernel<kCS, true, 2, 1, 1, 3>;
-        case 84: return encode_fast_kernel<kCS, true, 2, 1, 8, 4>; /* tensor-map staging */
-        case 34: return encode_fast_kernel<kCS, true, 2, 1, 3, 4>; /* diagnostics: no colour, no search */
-        case 44: return encode_fast_kernel<kCS, true, 2, 1, 4, 4>; /* diagnostics: no search */
-        case 54: return encode_fast_kernel<kCS, true, 2, 1, 5, 4>; /* diagnostics: no colour */
         default: break;
         }
     }

@@ -28,6 +28,11 @@ struct QuantDev {
     uint32_t smem_tables;             /* 1: stage thr (+bucket) in shared memory; 0: read from global */
     uint32_t smem_lut;                /* decode: 1 = stage the LUT in shared memory */
     const float *ctab;                /* chroma code -> u'/v' (LUV) or Cb/Cr (YCBCR), max_val_color + 1 entries */
+    /* direct search table for values known to lie in [1e-4, 1e8] (Lu'v' Y, XYZ): one 32-bit entry per key
+     * bucket, code = (dtab[(key >> d_shift) - d_lo] + key) >> 16 (luma_fast.cuh search_direct); NULL when the
+     * LUT does not qualify */
+    const uint32_t *dtab;
+    uint32_t d_shift, d_lo, d_n;
 };
 
 constexpr int kThreads = 256;

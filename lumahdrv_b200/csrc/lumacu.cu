@@ -83,6 +83,7 @@ struct lumacu_ctx {
     bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
     int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
+    bool no_direct = false;               /* tuning sweep / tests: bucket + threshold search even when the direct table exists */
 
     /* quantizer */
     bool configured = false;
@@ -524,11 +525,53 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
         }
     }
 
-    /* one device allocation: lut | thr | bucket | ctab */
+    /* Direct search table (tuned encode kernels, colour spaces whose searched values are clamped to
+     * [1e-4, 1e8]: Lu'v' luminance, XYZ).  For such a value the raw float bits `key` are an ordered key.  Cut the
+     * key range into buckets of 2^S keys holding at most ONE decision threshold each, and store per bucket
+     *     entry = (c0 << 16) + 0x10000 - thr_low - (bucket << S)        (mod 2^32)
+     * with c0 = number of thresholds below the bucket and thr_low = offset of the bucket's threshold inside it
+     * (2^S when it has none).  Then entry + key = (c0 << 16) + 0x10000 + (key_low - thr_low), whose upper half is
+     * c0 + 1 when key_low >= thr_low and c0 otherwise: code = (entry + key) >> 16 -- one shared-memory read and one
+     * add per sample.  NaN (canonical 0x7fffffff after the clamp) and anything an ulp above 1e8 are folded onto
+     * the 1e8 bucket by an unsigned min on the device, which needs every threshold to be <= 1e8.  The table starts
+     * one bucket below 1e-4 because a 2x2 mean of four 1e-4 samples may round an ulp below 1e-4. */
+    std::vector<uint32_t> dtab;
+    uint32_t d_shift = 0, d_lo = 0;
+    if (mode == SEARCH_BUCKET && thr[0] > 0x80000000u && max_val <= 32767u) {
+        const uint32_t k_lo = f2u(1e-4f), k_hi = f2u(1e8f);
+        if ((thr[max_val - 1] ^ 0x80000000u) <= k_hi) {
+            for (uint32_t S = 16; S >= 12 && dtab.empty(); S--) {
+                const uint32_t lo = (k_lo >> S) - 1u, n = (k_hi >> S) - lo + 1u;
+                if ((size_t)n * 4 > 48 * 1024)
+                    break;
+                bool ok = true;
+                for (uint32_t j = 1; j < max_val && ok; j++)
+                    ok = ((thr[j] ^ 0x80000000u) >> S) != ((thr[j - 1] ^ 0x80000000u) >> S);
+                if (!ok)
+                    continue;
+                dtab.resize(n);
+                uint32_t j = 0; /* thresholds below the current bucket */
+                for (uint32_t b = 0; b < n; b++) {
+                    const uint32_t kb = lo + b;
+                    while (j < max_val && ((thr[j] ^ 0x80000000u) >> S) < kb)
+                        j++;
+                    uint32_t thr_low = 1u << S;
+                    if (j < max_val && ((thr[j] ^ 0x80000000u) >> S) == kb)
+                        thr_low = (thr[j] ^ 0x80000000u) - (kb << S);
+                    dtab[b] = (j << 16) + 0x10000u - thr_low - (kb << S);
+                }
+                d_shift = S;
+                d_lo = lo;
+            }
+        }
+    }
+
+    /* one device allocation: lut | thr | bucket | ctab | dtab */
     const size_t off_thr = ((size_t)lut_len * 4 + 15) & ~(size_t)15;
     const size_t off_bucket = (off_thr + (size_t)thr_count * 4 + 15) & ~(size_t)15;
     const size_t off_ctab = (off_bucket + bucket.size() * 2 + 15) & ~(size_t)15;
-    const size_t total = off_ctab + ctab.size() * 4 + 16;
+    const size_t off_dtab = (off_ctab + ctab.size() * 4 + 15) & ~(size_t)15;
+    const size_t total = off_dtab + dtab.size() * 4 + 16;
     int rc = reserve(ctx, ctx->d_tables, total);
     if (rc)
         return rc;
@@ -542,12 +585,18 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
         CU_TRY(ctx, cudaMemcpy(d + off_bucket, bucket.data(), bucket.size() * 2, cudaMemcpyHostToDevice));
     if (!ctab.empty())
         CU_TRY(ctx, cudaMemcpy(d + off_ctab, ctab.data(), ctab.size() * 4, cudaMemcpyHostToDevice));
+    if (!dtab.empty())
+        CU_TRY(ctx, cudaMemcpy(d + off_dtab, dtab.data(), dtab.size() * 4, cudaMemcpyHostToDevice));
 
     QuantDev q{};
     q.lut = (const float *)d;
     q.thr = (const uint32_t *)(d + off_thr);
     q.bucket = (const uint16_t *)(d + off_bucket);
     q.ctab = ctab.empty() ? nullptr : (const float *)(d + off_ctab);
+    q.dtab = dtab.empty() ? nullptr : (const uint32_t *)(d + off_dtab);
+    q.d_shift = d_shift;
+    q.d_lo = d_lo;
+    q.d_n = (uint32_t)dtab.size();
     q.max_val = max_val;
     q.max_val_color = max_val_color;
     q.max_val_f = (float)max_val;
@@ -631,7 +680,8 @@ extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_varia
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (enc_variant < 0 || dec_variant < 0 || blocks_per_sm_cap < 0)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_tuning: negative argument");
-    ctx->enc_variant = enc_variant;
+    ctx->no_direct = enc_variant >= 1000; /* 1000 + variant: bucket + threshold search instead of the direct table */
+    ctx->enc_variant = enc_variant % 1000;
     ctx->dec_variant = dec_variant;
     ctx->grid_cap = blocks_per_sm_cap;
     return LUMACU_OK;
@@ -832,11 +882,21 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
         if (variant / 10 == 8 &&
             make_rgb_tensor_map(ctx, d_rgb, w, h, a.rgb_plane_stride, a.rgb_frame_stride, n_frames, a.rgb_tmap) != LUMACU_OK)
             variant = kEncVariantPlain;
-        fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk, variant);
+        /* walk 0 = direct search table (one LDS per sample); otherwise bucket heads + <= walk threshold compares */
+        const bool direct = ctx->q.dtab && (ctx->color_space == CS_LUV || ctx->color_space == CS_XYZ) && !ctx->no_direct;
+        int walk = direct ? 0 : (int)ctx->q.walk;
+        fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
+        if (!fn && direct) { /* tuning variants exist for one search flavour only */
+            walk = (int)ctx->q.walk;
+            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
+        }
         if (!fn && variant != kEncVariantPlain) {
             variant = kEncVariantPlain;
-            fn = pick_enc_fast(ctx->color_space, sub, bytes, (int)ctx->q.walk, variant);
+            walk = direct ? 0 : (int)ctx->q.walk;
+            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
         }
+        if (fn && walk == 0)
+            smem = (size_t)ctx->q.d_n * 4;
         if (fn && staged && variant != kEncVariantPlain)
             smem += kEncStagedSmemBytes;
     }

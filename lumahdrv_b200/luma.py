@@ -102,6 +102,16 @@ class Context:
         """0 = tuned kernels when their preconditions hold (default), 1 = generic kernels only."""
         check(self._lib.lumacu_set_kernel_path(self.handle, int(path)), self.handle, "lumacu_set_kernel_path")
 
+    def set_tuning(self, enc_variant: int = 0, dec_variant: int = 0, blocks_per_sm_cap: int = 0) -> None:
+        """lumacu_set_tuning: pick an instantiation of the tuned kernels (0 = default; 1000 + v = bucket/threshold
+        luma search instead of the direct table).  Every variant produces identical bits."""
+        check(self._lib.lumacu_set_tuning(self.handle, int(enc_variant), int(dec_variant), int(blocks_per_sm_cap)),
+              self.handle, "lumacu_set_tuning")
+
+    def set_host_bands(self, bands: int) -> None:
+        """Row bands per host-pointer call (0 = automatic)."""
+        check(self._lib.lumacu_set_host_bands(self.handle, int(bands)), self.handle, "lumacu_set_host_bands")
+
     @property
     def last_kernel_path(self) -> int:
         """1 if the last encode/decode launch ran a tuned kernel, 0 if it ran a generic one."""

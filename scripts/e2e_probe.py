@@ -25,7 +25,7 @@ h_in.copy_(torch.from_numpy((0.005 * np.power(2.0e6, rng.random((3, H, W), dtype
 frame = h_in.numpy()
 strides = L.vpx_strides(W, 2)
 planes = [[torch.empty((ph, s), dtype=torch.uint8).pin_memory().numpy() for (pw, ph), s in zip(L.plane_dims(W, H, 2), strides)]
-          for _ in range(2)]
+          for _ in range(6)]
 outs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
 
 
@@ -64,10 +64,59 @@ def t_both():
     return (time.perf_counter() - t0) / N * 1e3, res
 
 
-for nb in (1, 2, 4, 8, 16):
+for nb in (1, 2, 8):
     bands(nb)
     t_enc(); t_dec()
     e, d = t_enc(), t_dec()
     both, res = t_both()
     print(f"bands {nb:2d}: encode {e:6.3f} ms  decode {d:6.3f} ms  concurrent (independent loops) {both:6.3f} ms per frame pair "
           f"(enc {res['e']:.3f}, dec {res['d']:.3f})", flush=True)
+
+# ---- the bench's pipeline: encoder thread -> queue -> decoder thread, two plane slots
+import queue
+
+
+def pipelined(nframes, nslots=2):
+    free_q, full_q = queue.Queue(), queue.Queue()
+    for i in range(nslots):
+        free_q.put(i)
+    te, td, we, wd = [], [], [], []
+
+    def e():
+        for i in range(nframes):
+            t0 = time.perf_counter()
+            s = free_q.get()
+            t1 = time.perf_counter()
+            enc.encode(frame, planes[s])
+            t2 = time.perf_counter()
+            full_q.put(s)
+            we.append(t1 - t0); te.append(t2 - t1)
+        full_q.put(None)
+
+    def d():
+        k = 0
+        while True:
+            t0 = time.perf_counter()
+            s = full_q.get()
+            if s is None:
+                return
+            t1 = time.perf_counter()
+            dec.m_frame = outs[k & 1]
+            dec.decode(planes[s], W, H)
+            t2 = time.perf_counter()
+            free_q.put(s)
+            wd.append(t1 - t0); td.append(t2 - t1)
+            k += 1
+    t0 = time.perf_counter()
+    a, b = threading.Thread(target=e), threading.Thread(target=d)
+    a.start(); b.start(); a.join(); b.join()
+    tot = (time.perf_counter() - t0) / nframes * 1e3
+    ms = lambda v: 1e3 * sum(v[2:]) / max(1, len(v) - 2)
+    return tot, ms(te), ms(td), ms(we), ms(wd)
+
+
+for nb, ns in ((1, 2), (1, 3), (1, 4), (1, 6), (2, 2), (2, 4), (2, 6), (8, 4)):
+    bands(nb)
+    pipelined(6, ns)
+    tot, te, td, we, wd = pipelined(24, ns)
+    print(f"pipelined bands {nb} slots {ns}: {tot:6.3f} ms per frame | encode call {te:.3f} (waited {we:.3f}) | decode call {td:.3f} (waited {wd:.3f})", flush=True)

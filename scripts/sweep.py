@@ -21,8 +21,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--enc", default="0,2,3,4,12,13,14")
-    ap.add_argument("--dec", default="0,3,4,5,13,14,15")
+    ap.add_argument("--enc", default="0,1004,3,5,84,34,44,54")
+    ap.add_argument("--dec", default="0,3,5,14")
     ap.add_argument("--caps", default="0")
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)

@@ -59,8 +59,11 @@ def check_frame(L, po, frame, enc, o, profile, sc, cs, strides=None):
 
     # both kernel families (tuned where its preconditions hold, and the generic transcription) without the
     # reference's in-place side effect, then once more with it (always the generic kernel)
-    for path in (0, 1):
-        enc.m_quant.ctx.set_kernel_path(path)
+    # path 0 = tuned kernel with its default luma search (direct table where the LUT qualifies), 2 = tuned kernel
+    # forced onto the bucket + threshold search, 1 = generic kernel
+    for path in (0, 2, 1):
+        enc.m_quant.ctx.set_kernel_path(1 if path == 1 else 0)
+        enc.m_quant.ctx.set_tuning(1000 if path == 2 else 0)
         enc.strict_side_effect = False
         f_in = frame.copy()
         planes_path = L.alloc_planes(w, h, profile, strides, fill=0xAB)
@@ -69,6 +72,7 @@ def check_frame(L, po, frame, enc, o, profile, sc, cs, strides=None):
         assert bits_equal(f_in, frame), "input frame modified without strict_side_effect"
         KERNEL_PATHS_SEEN.add(("enc", path, enc.m_quant.ctx.last_kernel_path))
     enc.m_quant.ctx.set_kernel_path(0)
+    enc.m_quant.ctx.set_tuning(0)
     planes_gpu = L.alloc_planes(w, h, profile, strides, fill=0xAB)
     enc.strict_side_effect = True
     enc.encode(f_gpu, planes_gpu)
