@@ -158,6 +158,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kind: str, px_per_launch: float):
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture
+    (profiles/*_traffic.json, written by scripts/summarize_ncu.py), scaled to this run's pixels per launch."""
+    best = None
+    for p in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        try:
+            d = json.loads(p.read_text())
+            best = (d["kernels"][kind]["dram_bytes_per_pixel"] * px_per_launch, p.name)
+        except Exception:
+            continue
+    return best if best else (None, None)
+
+
 def ours_arm(args):
     import numpy as np
     import torch
@@ -292,7 +305,11 @@ def ours_arm(args):
         # frame i (each object has its own context and streams; ctypes releases the GIL inside the C call), so
         # both PCIe directions are busy.  Planes travel GPU -> host -> GPU like they would through VP9.
         import queue
-        slots = [[p.clone().pin_memory().numpy() for p in h_planes] for _ in range(2)]  # double-buffered host planes
+        # four host plane buffers between the two threads: with only two the stages run in lockstep and the decoder's
+        # small H2D copy queues behind the encoder's 100 MB one (3.8 ms per frame); with slack the loops settle
+        # into a phase where both PCIe directions stay busy (2.9 ms per frame; scripts/e2e_probe.py)
+        NSLOTS = 4
+        slots = [[p.clone().pin_memory().numpy() for p in h_planes] for _ in range(NSLOTS)]
         h_outs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
         free_q, full_q = queue.Queue(), queue.Queue()
         errors = []
@@ -324,8 +341,8 @@ def ours_arm(args):
         def e2e_run(nframes):
             while not free_q.empty():
                 free_q.get()
-            free_q.put(0)
-            free_q.put(1)
+            for i in range(NSLOTS):
+                free_q.put(i)
             te = threading.Thread(target=enc_thread, args=(nframes,))
             td = threading.Thread(target=dec_thread)
             te.start()
@@ -369,6 +386,7 @@ def ours_arm(args):
         dom = "encode_kernel" if enc_ms >= dec_ms else "decode_kernel"
         dom_ms = max(enc_ms, dec_ms)
         achieved = bytes_pass / (dom_ms / 1e3) / 1e9
+        traffic, traffic_src = measured_traffic("encode" if dom == "encode_kernel" else "decode", px_step)
         line = {
             "metric": "Mpixels/s encode+decode (PQ Lu'v' 4K float32)", "value": value, "unit": "Mpixels/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -378,7 +396,9 @@ def ours_arm(args):
                        "l2": f"inputs larger than L2: {F * (12 + 3 + 12) * W * H / 1e6:.0f} MB touched per step per GPU vs 126 MB L2",
                        "parallelism": f"frame shards x{world}, LUT broadcast only"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": (f"ncu --set full capture {traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
+                                            f"pixel x pixels per launch") if traffic else None,
                          "algorithmic_bytes_per_launch": bytes_pass, "kernel_ms": dom_ms,
                          "encode_ms": enc_ms, "decode_ms": dec_ms,
                          "encode_gbs": bytes_pass / (enc_ms / 1e3) / 1e9, "decode_gbs": bytes_pass / (dec_ms / 1e3) / 1e9,

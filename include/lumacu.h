@@ -235,7 +235,8 @@ int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
 /* Tuning sweep: pick one of the extra instantiations of the headline tuned kernels
  * (variant = 10 * PF + MINB: PF 1 = next tile prefetched into registers, MINB = resident blocks per SM
  * the register allocation is held to; 0 = the default) and optionally cap the resident blocks per SM
- * of the persistent grid (0 = whatever the occupancy calculator allows).  enc_variant + 1000 forces the
+ * of the persistent grid (0 = whatever the occupancy calculator allows; + 100 * T sizes the blocks of a
+ * multi-frame launch for T tiles per thread).  enc_variant + 1000 forces the
  * bucket + threshold luma search where the direct search table would be used.  Unknown variants fall back
  * to the default.  All variants produce identical bits. */
 int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap);

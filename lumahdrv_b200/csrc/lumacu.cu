@@ -83,6 +83,7 @@ struct lumacu_ctx {
     bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
     int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
+    int grid_tpt = 0;                     /* tuning sweep: tiles per thread of a multi-frame launch (0 = default) */
     bool no_direct = false;               /* tuning sweep / tests: bucket + threshold search even when the direct table exists */
 
     /* quantizer */
@@ -562,6 +563,7 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
                 }
                 d_shift = S;
                 d_lo = lo;
+                dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u); /* the kernels stage it with 128-bit loads */
             }
         }
     }
@@ -683,7 +685,8 @@ extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_varia
     ctx->no_direct = enc_variant >= 1000; /* 1000 + variant: bucket + threshold search instead of the direct table */
     ctx->enc_variant = enc_variant % 1000;
     ctx->dec_variant = dec_variant;
-    ctx->grid_cap = blocks_per_sm_cap;
+    ctx->grid_cap = blocks_per_sm_cap % 100;     /* blocks_per_sm_cap = cap + 100 * tiles_per_thread */
+    ctx->grid_tpt = blocks_per_sm_cap / 100;
     return LUMACU_OK;
 }
 
@@ -768,7 +771,11 @@ constexpr int kDecDefaultVariant = kDecVariantPlain;
 inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
 /* persistent grid: resident blocks on the whole chip, capped by the work */
-int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint32_t n_frames, uint32_t *gx)
+/* multi-frame launches: tiles per thread a block is sized for (sweep on B200, 4K frames: encode 8/16/32 tiles ->
+ * 654/642/641 us per 32 frames and 176/172/174 us per 8; decode 8/16/32 -> 645/649/687 us per 32 frames) */
+constexpr uint32_t kEncTilesPerThread = 16, kDecTilesPerThread = 8;
+
+int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint32_t n_frames, uint32_t tpt_default, uint32_t *gx)
 {
     /* occupancy (and the opt-in for > 48 KB of dynamic shared memory) is queried once per kernel and size */
     int per_sm = 0;
@@ -794,7 +801,8 @@ int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint
          * spreading the resident slots over all frames at once), with >= ~8 tiles per thread so that the
          * table staging stays amortised */
         uint32_t per_frame = (resident + n_frames - 1) / n_frames;
-        uint32_t coarse = (need + 7) / 8;
+        const uint32_t tpt = ctx->grid_tpt > 0 ? (uint32_t)ctx->grid_tpt : tpt_default;
+        uint32_t coarse = (need + tpt - 1) / tpt;
         g = std::max(per_frame, std::min(coarse, resident));
     }
     *gx = std::max(1u, std::min(g, need));
@@ -896,7 +904,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
             fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
         }
         if (fn && walk == 0)
-            smem = (size_t)ctx->q.d_n * 4;
+            smem = (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
         if (fn && staged && variant != kEncVariantPlain)
             smem += kEncStagedSmemBytes;
     }
@@ -905,7 +913,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
         fn = pick_enc(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
     uint32_t gx = 1;
-    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, &gx);
+    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, kEncTilesPerThread, &gx);
     if (rc)
         return rc;
     if (d_stats) {
@@ -988,7 +996,7 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
         fn = pick_dec(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);
     uint32_t gx = 1;
-    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, &gx);
+    rc = grid_for(ctx, (const void *)fn, smem, ntiles, n_frames, kDecTilesPerThread, &gx);
     if (rc)
         return rc;
     fn<<<dim3(gx, n_frames), kThreads, smem, st>>>(a);

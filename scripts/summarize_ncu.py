@@ -89,7 +89,7 @@ def launches(tag: str, rnd: str):
     print("wrote", out.name, "and launch summary")
 
 
-def full(tag: str, rnd: str):
+def full(tag: str, rnd: str, frames: int = 8):
     rep = ROOT / "gpurun_out" / f"{tag}_prof.ncu-rep"
     if not rep.exists():
         return
@@ -105,13 +105,25 @@ def full(tag: str, rnd: str):
                 i = hdr.index(m)
                 w.writerow([m, units[i]] + [r[i] for r in rows[2:]])
     print("wrote", out.name)
+    # DRAM traffic per launch of the two transform kernels (bench.py reports it as roofline.traffic, scaled per pixel)
+    names = [r[hdr.index("Kernel Name")] for r in rows[2:]]
+    rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tr = {"source": rep.name, "frames_per_launch": frames, "pixels_per_launch": frames * 3840 * 2160, "kernels": {}}
+    for r, nm in zip(rows[2:], names):
+        key = "encode" if "encode" in nm else "decode" if "decode" in nm else None
+        if key:
+            b = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
+            tr["kernels"][key] = {"kernel": short(nm), "dram_bytes_per_launch": b, "dram_bytes_per_pixel": b / tr["pixels_per_launch"]}
+    (ROOT / "profiles" / f"{rnd}_{tag}_traffic.json").write_text(json.dumps(tr, indent=1))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
     ap.add_argument("--round", default="r01")
+    ap.add_argument("--frames", type=int, default=8, help="frames per launch of the profiled bench run")
     a = ap.parse_args()
     (ROOT / "profiles").mkdir(exist_ok=True)
     launches(a.tag, a.round)
-    full(a.tag, a.round)
+    full(a.tag, a.round, a.frames)
