@@ -178,7 +178,8 @@ def ours_arm(args):
 
     import lumahdrv_b200 as L
     from lumahdrv_b200.device import DeviceTransform
-    from lumahdrv_b200.shard import broadcast_quantizer, frame_shard, pack_quantizer, unpack_quantizer
+    from lumahdrv_b200.shard import (broadcast_quantizer, frame_shard, pack_quantizer, packed_quantizer_size,
+                                     unpack_quantizer)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the transform has no CPU fallback)")
@@ -202,8 +203,8 @@ def ours_arm(args):
         if rank == 0:
             lut = L.build_lut(QUANT["ptf"], QUANT["ptfBitDepth"], QUANT["maxLum"], QUANT["minLum"])
             vec = pack_quantizer(lut, (1 << QUANT["colorBitDepth"]) - 1, L.CS_LUV, QUANT["maxLum"], QUANT["minLum"],
-                                 QUANT["preScaling"], QUANT["profile"])
-        got = unpack_quantizer(broadcast_quantizer(vec, 7 + n_lut, dev, src=0))
+                                 QUANT["preScaling"], QUANT["profile"], ptf=L.PTF_PQ)
+        got = unpack_quantizer(broadcast_quantizer(vec, packed_quantizer_size(QUANT["ptfBitDepth"]), dev, src=0))
         shared_lut = got["lut"]
     else:
         shared_lut = None

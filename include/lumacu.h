@@ -124,6 +124,33 @@ int lumacu_host_unregister(void *p);
 int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out,
                      size_t cap);
 
+/* ---- quantizer metadata wire format (host only) ---------------------------------- */
+/* The reference carries the quantizer from encoder to decoder as seven Matroska attachments whose payloads
+ * are the raw host bytes of the values (src/luma_encoder.cpp:78-106, read back at src/luma_decoder.cpp:79-122):
+ *   430 u32 ptfBitDepth | 431 u32 colorBitDepth | 432 i32 ptf | 433 i32 colorSpace |
+ *   434 float[maxVal] the LUT WITHOUT its last entry (getSize() = maxVal floats are written) |
+ *   435 float preScaling | 436 float[2] {maxLum, minLum}
+ * lumacu_metadata_pack writes them back to back as records {u32 id, u32 size, payload} (little endian) so that
+ * a worker can be configured from a byte stream without libmatroska; lumacu_metadata_unpack does what
+ * LumaDecoder::initialize does: take the scalars, rebuild the table from them (lumacu_build_lut) and overlay
+ * the stored entries.  Records with other ids are skipped; 430..434 are mandatory like in the reference. */
+typedef struct lumacu_metadata {
+    uint32_t ptf_bit_depth;
+    uint32_t color_bit_depth;
+    int32_t ptf;          /* lumacu_ptf */
+    int32_t color_space;  /* lumacu_color_space */
+    float pre_scaling;
+    float max_lum;
+    float min_lum;
+} lumacu_metadata;
+/* lut = the encoder's table (2^ptf_bit_depth entries, e.g. from lumacu_build_lut).  Returns the number of
+ * bytes needed in *used (also when blob is NULL or cap is too small: LUMACU_ERR_INVALID_ARGUMENT then). */
+int lumacu_metadata_pack(const lumacu_metadata *m, const float *lut, uint32_t lut_len, uint8_t *blob, size_t cap,
+                         size_t *used);
+/* lut_out receives 2^ptf_bit_depth entries (capacity lut_cap floats); *lut_len is set to that count. */
+int lumacu_metadata_unpack(const uint8_t *blob, size_t size, lumacu_metadata *m, float *lut_out, size_t lut_cap,
+                           uint32_t *lut_len);
+
 /* Host-side analysis of LumaQuantizer::quantize's luma branch
  * (src/luma_quantizer.cpp:219-235).  For a finite, strictly increasing LUT the
  * reference's "bisect, then pick the nearer neighbour with fp32 differences" is

@@ -38,6 +38,12 @@ class FrameStats(C.Structure):
     _fields_ = [("sum", C.c_double), ("max", C.c_float), ("min", C.c_float)]
 
 
+class Metadata(C.Structure):
+    """lumacu_metadata: the scalars of Matroska attachments 430..433, 435, 436 (include/lumacu.h)."""
+    _fields_ = [("ptf_bit_depth", C.c_uint32), ("color_bit_depth", C.c_uint32), ("ptf", C.c_int32), ("color_space", C.c_int32),
+                ("pre_scaling", C.c_float), ("max_lum", C.c_float), ("min_lum", C.c_float)]
+
+
 def build_library(force: bool = False) -> Path:
     """Compile liblumacu.so for sm_100a (nvcc cross-compiles without a GPU)."""
     if force or not LIB_PATH.exists():
@@ -65,6 +71,8 @@ SIGNATURES = {
     "lumacu_stream": (_P, [_P]),
     "lumacu_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "lumacu_host_free": (C.c_int, [_P]),
+    "lumacu_metadata_pack": (C.c_int, [C.POINTER(Metadata), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lumacu_metadata_unpack": (C.c_int, [_P, C.c_size_t, C.POINTER(Metadata), _P, C.c_size_t, C.POINTER(C.c_uint32)]),
     "lumacu_build_lut": (C.c_int, [C.c_int, C.c_uint, C.c_float, C.c_float, _P, C.c_size_t]),
     "lumacu_derive_thresholds": (C.c_int, [_P, C.c_uint32, _P]),
     "lumacu_plan_buckets": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),

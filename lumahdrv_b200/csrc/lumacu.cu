@@ -345,6 +345,88 @@ extern "C" int lumacu_plan_buckets(const uint32_t *thr_keys, uint32_t n_thr, uin
     return 0;
 }
 
+/* ================================ metadata wire format =============================== */
+
+namespace {
+void put_record(uint8_t *&p, uint32_t id, const void *payload, uint32_t size)
+{
+    memcpy(p, &id, 4);
+    memcpy(p + 4, &size, 4);
+    memcpy(p + 8, payload, size);
+    p += 8 + size;
+}
+} // namespace
+
+extern "C" int lumacu_metadata_pack(const lumacu_metadata *m, const float *lut, uint32_t lut_len, uint8_t *blob, size_t cap,
+                                    size_t *used)
+{
+    if (!m || !lut || lut_len < 1 || !used)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_pack: NULL argument");
+    const uint32_t table_bytes = (lut_len - 1) * 4u; /* getSize() = maxVal floats, one short of the table */
+    const size_t need = 7 * 8 + 4 + 4 + 4 + 4 + (size_t)table_bytes + 4 + 8;
+    *used = need;
+    if (!blob || cap < need)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_pack: need %zu bytes", need);
+    uint8_t *p = blob;
+    put_record(p, 430, &m->ptf_bit_depth, 4);
+    put_record(p, 431, &m->color_bit_depth, 4);
+    put_record(p, 432, &m->ptf, 4);
+    put_record(p, 433, &m->color_space, 4);
+    put_record(p, 434, lut, table_bytes);
+    put_record(p, 435, &m->pre_scaling, 4);
+    const float range[2] = {m->max_lum, m->min_lum};
+    put_record(p, 436, range, 8);
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_metadata_unpack(const uint8_t *blob, size_t size, lumacu_metadata *m, float *lut_out, size_t lut_cap,
+                                      uint32_t *lut_len)
+{
+    if (!blob || !m || !lut_out || !lut_len)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_unpack: NULL argument");
+    /* defaults of LumaDecoderParams (include/luma/luma_decoder.h:60-70,112-120) for the optional records */
+    lumacu_metadata r{11, 8, LUMACU_PTF_PSI, LUMACU_CS_LUV, 1.0f, 1e4f, 0.005f};
+    unsigned have = 0;
+    const uint8_t *table = nullptr;
+    uint32_t table_bytes = 0;
+    for (size_t off = 0; off + 8 <= size;) {
+        uint32_t id, n;
+        memcpy(&id, blob + off, 4);
+        memcpy(&n, blob + off + 4, 4);
+        if (off + 8 + (size_t)n > size)
+            return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_unpack: record %u overruns the blob", id);
+        const uint8_t *pl = blob + off + 8;
+        off += 8 + (size_t)n;
+        const bool scalar_ok = n >= 4;
+        switch (id) {
+        case 430: if (scalar_ok) { memcpy(&r.ptf_bit_depth, pl, 4); have |= 1; } break;
+        case 431: if (scalar_ok) { memcpy(&r.color_bit_depth, pl, 4); have |= 2; } break;
+        case 432: if (scalar_ok) { memcpy(&r.ptf, pl, 4); have |= 4; } break;
+        case 433: if (scalar_ok) { memcpy(&r.color_space, pl, 4); have |= 8; } break;
+        case 434: table = pl; table_bytes = n; have |= 16; break;
+        case 435: if (scalar_ok) memcpy(&r.pre_scaling, pl, 4); break;
+        case 436: if (n >= 8) { memcpy(&r.max_lum, pl, 4); memcpy(&r.min_lum, pl + 4, 4); } break;
+        default: break;
+        }
+    }
+    if (have != 31u)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "Failed to locate Luma HDRv meta data"); /* src/luma_decoder.cpp:117 */
+    if (r.ptf_bit_depth < 1 || r.ptf_bit_depth > 16)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_unpack: PTF bit depth %u", r.ptf_bit_depth);
+    const size_t n_lut = (size_t)1 << r.ptf_bit_depth;
+    if (lut_cap < n_lut)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_unpack: table needs %zu floats", n_lut);
+    /* setQuantizer(...) then memcpy(getMapping(), mapping, mapping_size) (src/luma_decoder.cpp:121-122), without
+     * writing past the table */
+    const int rc = lumacu_build_lut(r.ptf, r.ptf_bit_depth, r.max_lum, r.min_lum, lut_out, lut_cap);
+    if (rc)
+        return rc;
+    memcpy(lut_out, table, std::min<size_t>(table_bytes, n_lut * 4));
+    *m = r;
+    *lut_len = (uint32_t)n_lut;
+    return LUMACU_OK;
+}
+
 /* ================================ context ============================================ */
 
 extern "C" int lumacu_create(int device, lumacu_ctx **out)

@@ -110,6 +110,16 @@ int main(int argc, char **argv)
         }
         encoder.finish();
 
+        /* the quantizer metadata as it went into the container (attachments 430..436, src/luma_encoder.cpp:78-106) */
+        {
+            MkvInterface reader;
+            reader.openRead(file);
+            binary *data = NULL;
+            unsigned int id = 0, size = 0;
+            for (unsigned int i = 0; reader.getAttachment(i, &data, id, size); i++)
+                printf("att %u size %u %08x\n", id, size, fnv(data, size));
+        }
+
         LumaDecoder decoder(file);
         for (int f = 0;; f++) {
             LumaFrame *frame = decoder.decode();

@@ -26,7 +26,7 @@ def _rank_main(rank, world, port, n_frames, out_dir):
     import torch.distributed as dist
 
     import lumahdrv_b200 as L
-    from lumahdrv_b200.shard import broadcast_quantizer, frame_shard, pack_quantizer, unpack_quantizer
+    from lumahdrv_b200.shard import broadcast_quantizer, frame_shard, pack_quantizer, packed_quantizer_size, unpack_quantizer
     from oracle import pyoracle as po
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -36,8 +36,9 @@ def _rank_main(rank, world, port, n_frames, out_dir):
         vec = None
         if rank == 0:
             lut = L.build_lut("PQ", bits, 1e4, 0.005)  # host libm, reference formula (lumacu_build_lut)
-            vec = pack_quantizer(lut, (1 << cbits) - 1, L.CS_LUV, 1e4, 0.005, 1.0, 2)
-        got = unpack_quantizer(broadcast_quantizer(vec, 7 + (1 << bits), torch.device("cpu"), src=0))
+            vec = pack_quantizer(lut, (1 << cbits) - 1, L.CS_LUV, 1e4, 0.005, 1.0, 2, ptf=L.PTF_PQ)
+        got = unpack_quantizer(broadcast_quantizer(vec, packed_quantizer_size(bits), torch.device("cpu"), src=0))
+        assert got["ptf"] == L.PTF_PQ and got["ptf_bit_depth"] == bits and got["color_bit_depth"] == cbits
         assert got["max_val_color"] == 255 and got["color_space"] == L.CS_LUV and got["profile"] == 2
         assert got["max_lum"] == 1e4 and abs(got["min_lum"] - 0.005) < 1e-9 and got["pre_scaling"] == 1.0
 
