@@ -239,6 +239,17 @@ int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t
 int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch,
                           void *stream);
 
+/* ---- frame sources on the device ---------------------------------------------- */
+/* ExrInterface::testFrame (src/exr_interface.cpp:50-70): the reference's synthetic HDR test pattern generated
+ * in device memory (3*w*h f32, planar), bit-identical to the host function. */
+int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, uint32_t h, void *stream);
+/* The pixel loop of ExrInterface::readFrame (src/exr_interface.cpp:73-143): interleaved half-float RGBA pixels
+ * (Imf::Rgba, 8 bytes each, device memory) -> planar f32 frame.  channels = Imf::RgbaChannels of the file:
+ * 1 (R), 2 (G), 4 (B) replicate one channel, 7 (RGB) / 15 (RGBA) copy three; anything else fails like the
+ * reference ("luminance only frames not yet supported"). */
+int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba_half, uint32_t w, uint32_t h, int channels,
+                                  float *d_rgb, void *stream);
+
 /* ---- introspection (used by bench.py / tests) -------------------------------- */
 /* Number of kernels this context has launched so far. */
 uint64_t lumacu_launch_count(const lumacu_ctx *ctx);

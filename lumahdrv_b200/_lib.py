@@ -81,6 +81,8 @@ SIGNATURES = {
     "lumacu_encode": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
                                 C.POINTER(FrameStats)]),
     "lumacu_decode": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
+    "lumacu_test_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P]),
+    "lumacu_half_rgba_to_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
     "lumacu_set_host_bands": (C.c_int, [_P, C.c_int]),
     "lumacu_host_register": (C.c_int, [_P, C.c_size_t]),
     "lumacu_host_unregister": (C.c_int, [_P]),

@@ -47,5 +47,7 @@ void launch_quantize(unsigned blocks, size_t smem, cudaStream_t st, const QuantD
 void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, const float *in, float *out, size_t n,
                        int use_lut);
 const void *quantize_kernel_ptr();
+void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
+void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);
 
 } // namespace lumacu

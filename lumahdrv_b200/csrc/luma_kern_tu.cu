@@ -86,6 +86,16 @@ void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, cons
 }
 
 const void *quantize_kernel_ptr() { return (const void *)quantize_kernel; }
+
+void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h)
+{
+    test_frame_kernel<<<blocks, kThreads, 0, st>>>(rgb, w, h);
+}
+
+void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode)
+{
+    half_rgba_to_frame_kernel<<<blocks, kThreads, 0, st>>>((const uint2 *)rgba, rgb, n, mode);
+}
 #endif
 
 #else /* LUMA_TU_FAST */

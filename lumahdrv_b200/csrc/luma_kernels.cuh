@@ -20,6 +20,8 @@
  */
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "luma_device.cuh"
 #include "luma_kernels_decl.cuh"
 
@@ -585,6 +587,60 @@ __global__ void __launch_bounds__(kThreads) dequantize_kernel(const QuantDev q, 
             r = dequantize_chroma(v, q.max_val_color_f);
         }
         out[i] = r;
+    }
+}
+
+/* ---- frame sources on the device ------------------------------------------------------ */
+/* ExrInterface::testFrame (src/exr_interface.cpp:50-70): the reference's synthetic HDR pattern, written straight
+ * into HBM.  Integer sub-expressions are size_t / unsigned divisions in the reference; every float operation is a
+ * separately rounded IEEE mul or div in the reference's left-to-right order, e.g.
+ * 10000.0f*((float)(x*x))/(w*w) = ((1e4f * float(x*x)) / float(w*w)) with w*w an unsigned int product. */
+__global__ void __launch_bounds__(kThreads) test_frame_kernel(float *rgb, uint32_t w, uint32_t h)
+{
+    const size_t n = (size_t)w * h;
+    const float ww = (float)(uint32_t)(w * w), hh = (float)(uint32_t)(h * h); /* unsigned int products, as in the reference */
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const unsigned long long y = i / w, x = i - y * w;
+        float r, g, b;
+        if (y < h / 5) {
+            const float v = (y < h / 10) ? __fdiv_rn(__fmul_rn(10000.0f, (float)(x * x)), ww)
+                                         : __fdiv_rn(__fmul_rn(10000.0f, (float)((20ull * x) / w)), 20.0f);
+            r = g = b = v;
+        } else {
+            const unsigned long long band = (20ull * y / h) % 2ull, col = (30ull * x / w) % 2ull;
+            r = __fmul_rn(10000.0f, (float)(band ^ col));
+            const float on = __fmul_rn(10000.0f, (float)band);
+            g = __fdiv_rn(__fmul_rn(on, (float)(y * y)), hh);
+            b = __fdiv_rn(__fmul_rn(on, (float)(x * x)), ww);
+        }
+        __stcs(rgb + i, r);
+        __stcs(rgb + n + i, g);
+        __stcs(rgb + 2 * n + i, b);
+    }
+}
+
+/* ExrInterface::readFrame's pixel loop (src/exr_interface.cpp:73-143): interleaved half-float RGBA (Imf::Rgba, 8
+ * bytes per pixel) to the planar f32 LumaFrame layout; mode = Imf::RgbaChannels of the file: WRITE_R (1), WRITE_G
+ * (2), WRITE_B (4) replicate that channel into all three planes, WRITE_RGB (7) / WRITE_RGBA (15) copy r, g, b.
+ * half -> float is exact.  One thread converts two pixels (one 128-bit load). */
+__device__ __forceinline__ float half_bits_to_float(uint32_t h16)
+{
+    return __half2float(__ushort_as_half((unsigned short)h16));
+}
+__global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint2 *rgba, float *rgb, size_t n, int mode)
+{
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const uint2 v = __ldcs(rgba + i);
+        float r = half_bits_to_float(v.x & 0xffffu), g = half_bits_to_float(v.x >> 16), b = half_bits_to_float(v.y & 0xffffu);
+        if (mode == 1)
+            g = b = r;
+        else if (mode == 2)
+            r = b = g;
+        else if (mode == 4)
+            r = g = b;
+        __stcs(rgb + i, r);
+        __stcs(rgb + n + i, g);
+        __stcs(rgb + 2 * n + i, b);
     }
 }
 

@@ -1087,6 +1087,45 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     return LUMACU_OK;
 }
 
+/* ---- frame sources on the device ------------------------------------------------------------------------ */
+extern "C" int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, uint32_t h, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!d_rgb || !w || !h)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_test_frame_dev: NULL frame or empty size");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t n = (size_t)w * h;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    launch_test_frame(blocks, st, d_rgb, w, h);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba_half, uint32_t w, uint32_t h, int channels,
+                                             float *d_rgb, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!d_rgba_half || !d_rgb || !w || !h)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_half_rgba_to_frame_dev: NULL pointer or empty size");
+    if (channels != 1 && channels != 2 && channels != 4 && channels != 7 && channels != 15)
+        /* src/exr_interface.cpp:138-140 */
+        return fail(ctx, LUMACU_ERR_UNSUPPORTED, "Reading of luminance only frames not yet supported");
+    if (!aligned(d_rgba_half, 8))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_half_rgba_to_frame_dev: pixels must be 8-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t n = (size_t)w * h;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    launch_half_rgba_to_frame(blocks, st, d_rgba_half, d_rgb, n, channels);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
 extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame, uint32_t w, uint32_t h, int to_cs, float sc,
                                                 void *stream)
 {

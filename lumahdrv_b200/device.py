@@ -98,6 +98,27 @@ class DeviceTransform:
                                           3 * h * w, fstr, _stream_ptr(self.device)), hnd, "lumacu_decode_dev")
         return out
 
+    # ------------------------------------------------------------------ frame sources
+    def test_frame(self, w: int, h: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """ExrInterface::testFrame(frame, w, h) generated in device memory ([3, h, w] f32)."""
+        if out is None:
+            out = torch.empty((3, h, w), dtype=torch.float32, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_test_frame_dev(hnd, out.data_ptr(), w, h, _stream_ptr(self.device)), hnd, "lumacu_test_frame_dev")
+        return out
+
+    def half_rgba_to_frame(self, rgba: torch.Tensor, channels: int = 7, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[h, w, 4] float16 (Imf::Rgba pixels) -> [3, h, w] f32, like ExrInterface::readFrame's pixel loop."""
+        if rgba.dtype != torch.float16 or rgba.dim() != 3 or rgba.shape[2] != 4 or not rgba.is_contiguous() or not rgba.is_cuda:
+            raise LumaException("rgba must be a contiguous CUDA float16 [h, w, 4] tensor", 1)
+        h, w, _ = rgba.shape
+        if out is None:
+            out = torch.empty((3, h, w), dtype=torch.float32, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_half_rgba_to_frame_dev(hnd, rgba.data_ptr(), w, h, int(channels), out.data_ptr(),
+                                                      _stream_ptr(self.device)), hnd, "lumacu_half_rgba_to_frame_dev")
+        return out
+
     @property
     def launch_count(self) -> int:
         return self.quant.ctx.launch_count

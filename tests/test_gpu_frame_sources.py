@@ -1,0 +1,61 @@
+"""GPU (-m gpu): frame sources on the device against the oracle's restatement of
+ExrInterface::testFrame (src/exr_interface.cpp:50-70; its 256x256 output is pinned by the survey's hash b2082ac1)
+and against numpy for the exact half -> float conversion of ExrInterface::readFrame's pixel loop."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dt(lumalib):
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+    assert torch.cuda.is_available()
+    return DeviceTransform(0)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (1920, 1080), (250, 103), (7, 5), (3840, 2160)])
+def test_test_frame_bit_exact(dt, po, golden, w, h):
+    got = dt.test_frame(w, h).cpu().numpy()
+    ref = po.test_frame(w, h)
+    assert got.shape == ref.shape == (3, h, w)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    if (w, h) == (256, 256):
+        assert "%08x" % po.fnv1a32(got) == golden["frames"]["cfg1_256_pq_luv"]["input"] == "b2082ac1"
+
+
+def test_test_frame_feeds_encode_without_a_host_copy(dt, po, golden):
+    """testFrame on the device -> encode on the device: the survey's plane hashes of the 1080p config."""
+    import torch
+    w, h = 1920, 1080
+    frame = dt.test_frame(w, h)
+    planes = dt.encode(frame[None])
+    got = [p[0].cpu().numpy() for p in planes]
+    assert ["%08x" % v for v in po.plane_hashes(got, w, h, 2)] == golden["frames"]["cfg2_1080p_pq_luv"]["planes"]
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("channels", [7, 15, 1, 2, 4])
+def test_half_rgba_to_frame(dt, channels):
+    import torch
+    h, w = 123, 250
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 1 << 16, size=(h, w, 4), dtype=np.uint16)  # every half pattern incl. inf / nan / subnormals
+    px = bits.view(np.float16)
+    got = dt.half_rgba_to_frame(torch.from_numpy(px).cuda(), channels).cpu().numpy()
+    f = px.astype(np.float32)
+    if channels in (7, 15):
+        ref = np.stack([f[..., 0], f[..., 1], f[..., 2]])
+    else:
+        c = {1: 0, 2: 1, 4: 2}[channels]
+        ref = np.stack([f[..., c]] * 3)
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])
+
+
+def test_half_rgba_rejects_luminance_only(dt, lumalib):
+    import torch
+    with pytest.raises(lumalib.LumaException, match="luminance only"):
+        dt.half_rgba_to_frame(torch.zeros((4, 4, 4), dtype=torch.float16, device="cuda"), channels=16)
