@@ -111,6 +111,24 @@ __device__ __forceinline__ float pq_decode(float val, float l_max)
     return __fmul_rn(l_max, powf_glibc(__fdiv_rn(num, den), inv_n));
 }
 
+/* BT.2020 Y'CbCr of one pixel (src/luma_quantizer.cpp:317-354): eight exact powf evaluations.  Deliberately NOT
+ * inlined: a tile holds 8 pixels, and 64 inlined copies of the powf sequence (~100 instructions each) made the
+ * kernels instruction-fetch bound (ncu: "no_instruction" was the top stall).  One copy, called per pixel, with
+ * the three PQ curves of a pixel interleaved inside it. */
+static __device__ __noinline__ float3 ycbcr_forward_px(float R, float G, float B, float l_max)
+{
+    /* std::max(v, 1e-10f) with v first: NaN stays NaN */
+    const float Rp = pq_encode(max_nan(R, 1e-10f), l_max);
+    const float Gp = pq_encode(max_nan(G, 1e-10f), l_max);
+    const float Bp = pq_encode(max_nan(B, 1e-10f), l_max);
+    const float y = dot3(0.2627f, 0.6780f, 0.0593f, Rp, Gp, Bp);
+    float3 c;
+    c.x = pq_decode(__fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y), 16.0f), 255.0f), l_max);
+    c.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp, y), 1.8814f)), 128.0f), 255.0f);
+    c.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp, y), 1.4746f)), 128.0f), 255.0f);
+    return c;
+}
+
 /* ---- forward colour transform of one pixel (src/luma_quantizer.cpp:269-373) ---- */
 template <int CS>
 __device__ __forceinline__ void color_forward(float R, float G, float B, float l_max, float &c0, float &c1,
@@ -134,14 +152,10 @@ __device__ __forceinline__ void color_forward(float R, float G, float B, float l
         c1 = div_const_int<255>(__fmul_rn(__fdiv_rn(__fmul_rn(4.0f, x), den), 410.0f));
         c2 = div_const_int<255>(__fmul_rn(__fdiv_rn(__fmul_rn(9.0f, y), den), 410.0f));
     } else if (CS == CS_YCBCR) {
-        /* std::max(v, 1e-10f) with v first: NaN stays NaN */
-        float Rp = pq_encode(max_nan(R, 1e-10f), l_max);
-        float Gp = pq_encode(max_nan(G, 1e-10f), l_max);
-        float Bp = pq_encode(max_nan(B, 1e-10f), l_max);
-        float y = dot3(0.2627f, 0.6780f, 0.0593f, Rp, Gp, Bp);
-        c0 = pq_decode(__fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y), 16.0f), 255.0f), l_max);
-        c1 = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp, y), 1.8814f)), 128.0f), 255.0f);
-        c2 = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp, y), 1.4746f)), 128.0f), 255.0f);
+        const float3 c = ycbcr_forward_px(R, G, B, l_max);
+        c0 = c.x;
+        c1 = c.y;
+        c2 = c.z;
     } else { /* CS_RGB */
         c0 = R;
         c1 = G;
@@ -180,6 +194,36 @@ __device__ __forceinline__ ChromaInv chroma_inverse(float c1, float c2)
     return r;
 }
 
+/* BT.2020 Y'CbCr -> linear RGB once y = ((255 PQenc(L)) - 16) / 219 is known (src/luma_quantizer.cpp:449-459).  The
+ * tuned decode kernel reads y from a host-built per-code table instead of evaluating PQenc per pixel. */
+static __device__ __noinline__ float ycbcr_luma_term(float c0, float l_max) /* ((255 PQenc(L)) - 16) / 219 */
+{
+    const float y = pq_encode(c0, l_max);
+    return __fdiv_rn(__fsub_rn(__fmul_rn(255.0f, y), 16.0f), 219.0f);
+}
+static __device__ __noinline__ float3 ycbcr_inverse_px(float y, float ca, float cb, float l_max) /* one copy, see ycbcr_forward_px */
+{
+    float blue = __fadd_rn(y, ca);
+    float red = __fadd_rn(y, cb);
+    float green = __fdiv_rn(__fsub_rn(__fsub_rn(y, __fmul_rn(0.2627f, red)), __fmul_rn(0.0593f, blue)), 0.6780f);
+    /* std::max(0.0f, std::min(1.0f, v)): NaN -> 1 */
+    red = clamp01_std(red);
+    green = clamp01_std(green);
+    blue = clamp01_std(blue);
+    float3 o;
+    o.x = pq_decode(red, l_max);
+    o.y = pq_decode(green, l_max);
+    o.z = pq_decode(blue, l_max);
+    return o;
+}
+__device__ __forceinline__ void ycbcr_inverse_from_y(float y, ChromaInv ch, float l_max, float &R, float &G, float &B)
+{
+    const float3 o = ycbcr_inverse_px(y, ch.a, ch.b, l_max);
+    R = o.x;
+    G = o.y;
+    B = o.z;
+}
+
 template <int CS>
 __device__ __forceinline__ void color_inverse(float c0, ChromaInv ch, float l_max, float &R, float &G, float &B)
 {
@@ -195,19 +239,7 @@ __device__ __forceinline__ void color_inverse(float c0, ChromaInv ch, float l_ma
         G = dot3(LUMA_I10, LUMA_I11, LUMA_I12, c0, ch.a, ch.b);
         B = dot3(LUMA_I20, LUMA_I21, LUMA_I22, c0, ch.a, ch.b);
     } else if (CS == CS_YCBCR) {
-        float y = pq_encode(c0, l_max);
-        y = __fdiv_rn(__fsub_rn(__fmul_rn(255.0f, y), 16.0f), 219.0f);
-        float blue = __fadd_rn(y, ch.a);
-        float red = __fadd_rn(y, ch.b);
-        float green =
-            __fdiv_rn(__fsub_rn(__fsub_rn(y, __fmul_rn(0.2627f, red)), __fmul_rn(0.0593f, blue)), 0.6780f);
-        /* std::max(0.0f, std::min(1.0f, v)): NaN -> 1 */
-        red = clamp01_std(red);
-        green = clamp01_std(green);
-        blue = clamp01_std(blue);
-        R = pq_decode(red, l_max);
-        G = pq_decode(green, l_max);
-        B = pq_decode(blue, l_max);
+        ycbcr_inverse_from_y(ycbcr_luma_term(c0, l_max), ch, l_max, R, G, B);
     } else {
         R = c0;
         G = ch.a;

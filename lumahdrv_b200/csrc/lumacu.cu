@@ -236,6 +236,15 @@ static float host_pq_decode(float val, float L)
     return L * powf(num / (c2 - c3 * Vp), 1.0f / n);
 }
 
+static float host_pq_encode(float val, float L)
+{
+    const float m = 78.8438, n = 0.1593, c1 = 0.8359, c2 = 18.8516, c3 = 18.6875;
+    volatile float Lp = powf(val / L, n);
+    volatile float num = c1 + c2 * Lp;
+    volatile float den = 1.0f + c3 * Lp;
+    return powf(num / den, m);
+}
+
 extern "C" int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out, size_t cap)
 {
     if (!lut_out || bitdepth > 16)
@@ -650,12 +659,26 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
         }
     }
 
-    /* one device allocation: lut | thr | bucket | ctab | dtab */
+    /* CS_YCBCR decode: per-code y' = ((255 PQenc(lut[code])) - 16) / 219 with the reference's own float expression
+     * (src/luma_quantizer.cpp:447-448, 493-494) and the host libm */
+    std::vector<float> ylut;
+    if (color_space == CS_YCBCR) {
+        ylut.resize(lut_len);
+        for (uint32_t i = 0; i < lut_len; i++) {
+            volatile float y = host_pq_encode(lut[i], max_lum);
+            volatile float t = 255.0f * y;
+            t = t - 16.0f;
+            ylut[i] = t / 219.0f;
+        }
+    }
+
+    /* one device allocation: lut | thr | bucket | ctab | dtab | ylut */
     const size_t off_thr = ((size_t)lut_len * 4 + 15) & ~(size_t)15;
     const size_t off_bucket = (off_thr + (size_t)thr_count * 4 + 15) & ~(size_t)15;
     const size_t off_ctab = (off_bucket + bucket.size() * 2 + 15) & ~(size_t)15;
     const size_t off_dtab = (off_ctab + ctab.size() * 4 + 15) & ~(size_t)15;
-    const size_t total = off_dtab + dtab.size() * 4 + 16;
+    const size_t off_ylut = (off_dtab + dtab.size() * 4 + 15) & ~(size_t)15;
+    const size_t total = off_ylut + ylut.size() * 4 + 16;
     int rc = reserve(ctx, ctx->d_tables, total);
     if (rc)
         return rc;
@@ -671,6 +694,8 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
         CU_TRY(ctx, cudaMemcpy(d + off_ctab, ctab.data(), ctab.size() * 4, cudaMemcpyHostToDevice));
     if (!dtab.empty())
         CU_TRY(ctx, cudaMemcpy(d + off_dtab, dtab.data(), dtab.size() * 4, cudaMemcpyHostToDevice));
+    if (!ylut.empty())
+        CU_TRY(ctx, cudaMemcpy(d + off_ylut, ylut.data(), ylut.size() * 4, cudaMemcpyHostToDevice));
 
     QuantDev q{};
     q.lut = (const float *)d;
@@ -681,6 +706,7 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
     q.d_shift = d_shift;
     q.d_lo = d_lo;
     q.d_n = (uint32_t)dtab.size();
+    q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
     q.max_val = max_val;
     q.max_val_color = max_val_color;
     q.max_val_f = (float)max_val;

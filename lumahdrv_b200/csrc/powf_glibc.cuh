@@ -48,21 +48,22 @@ static __device__ const unsigned long long k_exp2f_tab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 
-__device__ __forceinline__ float powf_glibc(float x, float y)
-{
-    uint32_t ix = __float_as_uint(x);
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
-        /* x < 0x1p-126, or inf, or nan (e_powf.c "zeroinfnan (ix)" and below) */
-        if (2u * ix - 1u >= 2u * 0x7f800000u - 1u)
-            return __fmul_rn(x, x); /* +-0 -> +0, +-inf -> +inf, nan -> nan (y > 0, not an odd integer) */
-        if (ix & 0x80000000u)
-            return __int_as_float(0x7fffffff); /* finite x < 0, non-integer y: invalid */
-        /* normalise a subnormal x so that the exponent goes negative */
-        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));
-        ix &= 0x7fffffffu;
-        ix -= 23u << 23;
-    }
+/* Polynomial coefficients live in constant memory so that DMUL / DADD take them as constant-bank operands; as
+ * literals the compiler rebuilt each 64-bit value with two UMOVs at every use (15 % of the instruction stream).
+ * [0..4] = __powf_log2_data.poly (A), [5..7] = __exp2f_data.poly_scaled (C). */
+static __constant__ double k_powf_poly[8] = {0x1.27616c9496e0bp-2, -0x1.71969a075c67ap-2, 0x1.ec70a6ca7baddp-2,
+                                             -0x1.7154748bef6c8p-1, 0x1.71547652ab82bp+0,
+                                             0x1.c6af84b912394p-5, 0x1.ebfce50fac4f3p-3,  0x1.62e42ff0c52d6p-1};
 
+/* Everything e_powf.c does before / instead of the main path: x zero, inf, nan, negative or subnormal.  Out of
+ * line and rare: in the PQ call sites x is a clamped positive number except for 0 (LUT entry 0) and NaN pixels. */
+static __device__ __noinline__ float powf_glibc_rare(float x, float y);
+
+/* Straight-line main path: rare inputs are detected up front and recomputed out of line at the end, results that
+ * overflow or underflow only override the value, so that the compiler can interleave the independent powf chains
+ * of a pixel (three PQ curves at a time) instead of serialising them behind branches. */
+__device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
+{
     /* log2_inline: x = 2^k z, z in [OFF, 2 OFF), c near the centre of z's subinterval */
     const uint32_t tmp = ix - 0x3f330000u;
     const int i = (int)((tmp >> (23 - 4)) & 15u);
@@ -72,8 +73,7 @@ __device__ __forceinline__ float powf_glibc(float x, float y)
     const double2 tc = k_powf_log2_tab[i];
     const double z = (double)__uint_as_float(iz);
 
-    const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2,
-                 A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
+    const double A0 = k_powf_poly[0], A1 = k_powf_poly[1], A2 = k_powf_poly[2], A3 = k_powf_poly[3], A4 = k_powf_poly[4];
     const double r = __dadd_rn(__dmul_rn(z, tc.x), -1.0);
     const double y0 = __dadd_rn(tc.y, (double)k);
     const double r2 = __dmul_rn(r, r);
@@ -85,19 +85,10 @@ __device__ __forceinline__ float powf_glibc(float x, float y)
     yy = __dadd_rn(__dmul_rn(yy, r4), q);
 
     const double ylogx = __dmul_rn((double)y, yy);
-    const uint32_t top16 = (uint32_t)(((unsigned long long)__double_as_longlong(ylogx) >> 47) & 0xffffu);
-    if (top16 >= (uint32_t)((unsigned long long)0x405f800000000000ull >> 47)) { /* |y log2 x| >= 126 */
-        if (ylogx > 0x1.fffffffd1d571p+6)
-            return __int_as_float(0x7f800000); /* overflow */
-        if (ylogx <= -150.0)
-            return 0.0f; /* underflow */
-        if (ylogx < -149.0)
-            return __int_as_float(0x00000001); /* __math_may_uflowf: 0x1.4p-75f squared */
-    }
 
     /* exp2_inline: x = k/N + r, |r| <= 1/(2N), N = 32 */
     const double SHIFT = 0x1.8p+47; /* 0x1.8p52 / N */
-    const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1;
+    const double C0 = k_powf_poly[5], C1 = k_powf_poly[6], C2 = k_powf_poly[7];
     double kd = __dadd_rn(ylogx, SHIFT);
     const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
     kd = __dadd_rn(kd, -SHIFT);
@@ -110,7 +101,43 @@ __device__ __forceinline__ float powf_glibc(float x, float y)
     double o = __dadd_rn(__dmul_rn(C2, rr), 1.0);
     o = __dadd_rn(__dmul_rn(zz, rr2), o);
     o = __dmul_rn(o, s);
-    return __double2float_rn(o);
+    float res = __double2float_rn(o);
+
+    const uint32_t hi = (uint32_t)__double2hiint(ylogx) & 0x7fff8000u;
+    if (__builtin_expect(hi >= 0x405f8000u, 0)) { /* |y log2 x| >= 126 */
+        if (ylogx > 0x1.fffffffd1d571p+6)
+            res = __int_as_float(0x7f800000); /* overflow */
+        else if (ylogx <= -150.0)
+            res = 0.0f; /* underflow */
+        else if (ylogx < -149.0)
+            res = __int_as_float(0x00000001); /* __math_may_uflowf: 0x1.4p-75f squared */
+    }
+    return res;
+}
+
+__device__ __forceinline__ float powf_glibc(float x, float y)
+{
+    const uint32_t ix = __float_as_uint(x);
+    const bool rare = ix - 0x00800000u >= 0x7f800000u - 0x00800000u; /* not a positive normal number */
+    float res = powf_glibc_main(rare ? 0x3f800000u : ix, y);
+    if (__builtin_expect(rare, 0))
+        res = powf_glibc_rare(x, y);
+    return res;
+}
+
+static __device__ __noinline__ float powf_glibc_rare(float x, float y)
+{
+    uint32_t ix = __float_as_uint(x);
+    /* x < 0x1p-126, or inf, or nan (e_powf.c "zeroinfnan (ix)" and below) */
+    if (2u * ix - 1u >= 2u * 0x7f800000u - 1u)
+        return __fmul_rn(x, x); /* +-0 -> +0, +-inf -> +inf, nan -> nan (y > 0, not an odd integer) */
+    if (ix & 0x80000000u)
+        return __int_as_float(0x7fffffff); /* finite x < 0, non-integer y: invalid */
+    /* normalise a subnormal x so that the exponent goes negative */
+    ix = __float_as_uint(__fmul_rn(x, 0x1p23f));
+    ix &= 0x7fffffffu;
+    ix -= 23u << 23;
+    return powf_glibc_main(ix, y);
 }
 
 } // namespace lumacu

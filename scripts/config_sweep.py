@@ -31,7 +31,10 @@ CONFIGS = [
 def main():
     dev = torch.device("cuda", 0)
     out = []
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, w, h, F, kw in CONFIGS:
+        if only and only not in name:
+            continue
         t = DeviceTransform(0, **kw)
         g = torch.Generator(device=dev).manual_seed(7)
         rgb = 0.005 * torch.pow(torch.tensor(2.0e6, device=dev), torch.rand((F, 3, h, w), generator=g, device=dev))
