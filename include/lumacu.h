@@ -239,6 +239,30 @@ int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t
 int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch,
                           void *stream);
 
+/* ---- display decode ------------------------------------------------------------- */
+/* What the reference's player does in its fragment shader (src/lumaplay_dequantizer.frag:70-157, parameters set
+ * at lumaplay.cpp:395-411): dequantise + inverse colour transform (here: exactly the LumaDecoder::decode path,
+ * nearest-neighbour chroma like the CPU decoder rather than the shader's bilinear texture fetch), then
+ *   RGB * exposure / scaling        (scaling = preScaling / user_scaling; or the 8-bit "LDR simulation")
+ *   optional sigmoid tone curve     v^0.8 / (v^0.8 + 0.8^0.8)
+ *   display gamma                   v^(1/gamma)
+ * into an 8-bit RGBA image (alpha = 255).  Floating-point pow makes this path approximate by nature, like the GLSL
+ * original; tests compare against a numpy restatement with a 1-LSB tolerance. */
+typedef struct lumacu_display_params {
+    float exposure;     /* lumaplay's exposure multiplier, 1 = none */
+    float gamma;        /* display gamma, e.g. 2.2 */
+    float user_scaling; /* lumaplay's userScaling, 1 = none */
+    int do_tmo;         /* sigmoid tone curve on/off */
+    int ldr_sim;        /* 8-bit LDR simulation on/off */
+} lumacu_display_params;
+int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                   uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
+                   uint8_t *rgba, int32_t rgba_pitch);
+int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
+                       uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
+                       uint8_t *d_rgba, int32_t rgba_pitch, uint32_t n_frames,
+                       const size_t plane_frame_stride[3], size_t rgba_frame_stride, void *stream);
+
 /* ---- frame sources on the device ---------------------------------------------- */
 /* ExrInterface::testFrame (src/exr_interface.cpp:50-70): the reference's synthetic HDR test pattern generated
  * in device memory (3*w*h f32, planar), bit-identical to the host function. */

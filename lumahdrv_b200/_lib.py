@@ -38,6 +38,11 @@ class FrameStats(C.Structure):
     _fields_ = [("sum", C.c_double), ("max", C.c_float), ("min", C.c_float)]
 
 
+class DisplayParams(C.Structure):
+    """lumacu_display_params (include/lumacu.h)."""
+    _fields_ = [("exposure", C.c_float), ("gamma", C.c_float), ("user_scaling", C.c_float), ("do_tmo", C.c_int), ("ldr_sim", C.c_int)]
+
+
 class Metadata(C.Structure):
     """lumacu_metadata: the scalars of Matroska attachments 430..433, 435, 436 (include/lumacu.h)."""
     _fields_ = [("ptf_bit_depth", C.c_uint32), ("color_bit_depth", C.c_uint32), ("ptf", C.c_int32), ("color_space", C.c_int32),
@@ -81,6 +86,9 @@ SIGNATURES = {
     "lumacu_encode": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
                                 C.POINTER(FrameStats)]),
     "lumacu_decode": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
+    "lumacu_display": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.POINTER(DisplayParams), _P, C.c_int32]),
+    "lumacu_display_dev": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.POINTER(DisplayParams), _P,
+                                     C.c_int32, C.c_uint32, _P, C.c_size_t, _P]),
     "lumacu_test_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P]),
     "lumacu_half_rgba_to_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
     "lumacu_set_host_bands": (C.c_int, [_P, C.c_int]),

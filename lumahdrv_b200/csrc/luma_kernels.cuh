@@ -393,6 +393,26 @@ __global__ void __launch_bounds__(kThreads) encode_kernel(const EncArgs a)
         finish_stats(a, frame, sum, mx, mn);
 }
 
+/* Display tail of the reference's player (src/lumaplay_dequantizer.frag:141-156) for one colour component:
+ *   ldrSim: v = exposure * max(1, min(256, floor(256 v / scaling))) / 256      else: v = v * exposure / scaling
+ *   doTmo:  v = v^0.8 / (v^0.8 + 0.8^0.8)                                      (sigmoid tone curve, n = sig = 0.8)
+ *   out    = v^(1/gamma), written to an 8-bit unorm framebuffer: clamp to [0, 1], round(255 v); NaN -> 0.
+ * Plain fp32 with CUDA's powf: like the GLSL original this is not a bit-exact path (tests allow 1 LSB). */
+__device__ __forceinline__ uint32_t display_unorm8(float v, const DecArgs &a)
+{
+    if (a.disp_ldr)
+        v = a.disp_exposure * fmaxf(1.0f, fminf(256.0f, floorf(256.0f * v / a.disp_scaling))) / 256.0f;
+    else
+        v = v * a.disp_exposure / a.disp_scaling;
+    if (a.disp_tmo) {
+        const float t = powf(v, 0.8f);
+        v = t / (t + 0.83651630373780790557f); /* 0.8^0.8 */
+    }
+    v = powf(v, a.disp_inv_gamma);
+    v = fminf(fmaxf(v, 0.0f), 1.0f); /* fmaxf drops NaN -> 0 */
+    return (uint32_t)__float2int_rn(v * 255.0f);
+}
+
 /* =============================== decode ========================================= */
 template <int CS, bool SUB, int BYTES, bool VEC>
 __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
@@ -513,6 +533,28 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
                 o[1][r][i] = G;
                 o[2][r][i] = B;
             }
+        }
+
+        if (a.rgba) { /* display mode: tone curve + gamma, 8-bit RGBA out */
+            uint8_t *img = a.rgba + (size_t)frame * a.rgba_frame_stride;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                uint32_t px[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    px[i] = display_unorm8(o[0][r][i], a) | (display_unorm8(o[1][r][i], a) << 8) |
+                            (display_unorm8(o[2][r][i], a) << 16) | 0xff000000u;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(img + (size_t)(y0 + r) * a.rgba_pitch) + x0;
+                if (VEC && (a.rgba_pitch & 15) == 0) {
+                    __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(px[0], px[1], px[2], px[3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((uint32_t)r < ny && (uint32_t)i < nx)
+                            dst[i] = px[i];
+                }
+            }
+            continue;
         }
 
 #pragma unroll

@@ -88,6 +88,13 @@ struct DecArgs {
     int prescale;
     float2 nz; /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
     int passthrough; /* generic kernels: stop after dequantisation + chroma replication (getVpxChannels) */
+    /* generic kernels, display mode (lumacu_display*): instead of storing the float frame, apply the display tail of
+     * the reference's player shader (src/lumaplay_dequantizer.frag:141-156) and store 8-bit RGBA */
+    uint8_t *rgba;        /* NULL = normal decode */
+    int32_t rgba_pitch;   /* bytes per output row */
+    size_t rgba_frame_stride;
+    float disp_exposure, disp_scaling, disp_inv_gamma;
+    int disp_tmo, disp_ldr;
 };
 
 } // namespace lumacu

@@ -81,6 +81,10 @@ struct lumacu_ctx {
     bool force_generic = false; /* tests: run the literal kernels */
     bool last_fast = false;     /* the last encode/decode launch used a tuned kernel */
     bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
+    const lumacu_display_params *display = nullptr; /* next decode launch is a display launch (set by lumacu_display_dev) */
+    uint8_t *display_rgba = nullptr;
+    int32_t display_pitch = 0;
+    size_t display_frame_stride = 0;
     int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
     int grid_tpt = 0;                     /* tuning sweep: tiles per thread of a multi-frame launch (0 = default) */
@@ -912,6 +916,8 @@ int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint
         const uint32_t tpt = ctx->grid_tpt > 0 ? (uint32_t)ctx->grid_tpt : tpt_default;
         uint32_t coarse = (need + tpt - 1) / tpt;
         g = std::max(per_frame, std::min(coarse, resident));
+    } else if (ctx->grid_tpt > 0) { /* tuning sweep: single-frame launches sized by tiles per thread */
+        g = std::min(resident, std::max(1u, (need + (uint32_t)ctx->grid_tpt - 1) / (uint32_t)ctx->grid_tpt));
     }
     *gx = std::max(1u, std::min(g, need));
     return LUMACU_OK;
@@ -1093,7 +1099,24 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     size_t smem = ctx->smem_dec;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
     a.passthrough = ctx->passthrough ? 1 : 0;
-    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !ctx->passthrough) {
+    if (ctx->display) {
+        a.rgba = ctx->display_rgba;
+        a.rgba_pitch = ctx->display_pitch;
+        a.rgba_frame_stride = ctx->display_frame_stride;
+        a.disp_exposure = ctx->display->exposure;
+        a.disp_scaling = pre_scaling / ctx->display->user_scaling; /* lumaplay.cpp:406 */
+        a.disp_inv_gamma = 1.0f / ctx->display->gamma;
+        a.disp_tmo = ctx->display->do_tmo ? 1 : 0;
+        a.disp_ldr = ctx->display->ldr_sim ? 1 : 0;
+        a.prescale = 0; /* the player folds preScaling into `scaling` instead of dividing the frame */
+        vec = (w % 4 == 0);
+        for (int p = 0; p < 3; p++) {
+            const size_t al = (size_t)((p && sub) ? 2 : 4) * bytes;
+            vec = vec && aligned(d_planes[p], al) && (strides[p] % al == 0) && (a.plane_frame_stride[p] % al == 0);
+        }
+        vec = vec && aligned(a.rgba, 16) && (a.rgba_frame_stride % 16 == 0);
+    }
+    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !ctx->passthrough && !ctx->display) {
         fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
         if (!fn)
             fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
@@ -1111,6 +1134,33 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
+}
+
+/* ---- display decode ------------------------------------------------------------------- */
+extern "C" int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
+                                  uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
+                                  uint8_t *d_rgba, int32_t rgba_pitch, uint32_t n_frames, const size_t plane_frame_stride[3],
+                                  size_t rgba_frame_stride, void *stream)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!params || !d_rgba)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: NULL pointer argument");
+    if (rgba_pitch < (int32_t)(w * 4) || (rgba_pitch & 3))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: rgba_pitch must be a multiple of 4 and >= 4*w");
+    if (!(params->gamma > 0.0f) || !(params->user_scaling > 0.0f))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: gamma and user_scaling must be positive");
+    if (!aligned(d_rgba, 4))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: rgba must be 4-byte aligned");
+    ctx->display = params;
+    ctx->display_rgba = d_rgba;
+    ctx->display_pitch = rgba_pitch;
+    ctx->display_frame_stride = rgba_frame_stride ? rgba_frame_stride : (size_t)rgba_pitch * h;
+    /* d_rgb is unused in display mode; pass the output buffer to satisfy the NULL check */
+    const int rc = lumacu_decode_dev(ctx, d_planes, strides, w, h, profile, pre_scaling, reinterpret_cast<float *>(d_rgba), n_frames,
+                                     0, plane_frame_stride, stream);
+    ctx->display = nullptr;
+    return rc;
 }
 
 /* ---- frame sources on the device ------------------------------------------------------------------------ */
@@ -1416,6 +1466,47 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
                                       ctx->s_out));
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
+                              int profile, float pre_scaling, const lumacu_display_params *params, uint8_t *rgba,
+                              int32_t rgba_pitch)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->configured)
+        return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_display: lumacu_set_quantizer has not been called");
+    if (!rgba || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display: NULL pointer argument");
+    int rc = check_profile(ctx, profile, w, h, false);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint32_t pw[3], ph[3];
+    plane_geometry(w, h, profile, pw, ph);
+    const int bytes = profile > 1 ? 2 : 1;
+    for (int p = 0; p < 3; p++)
+        if (strides[p] < (int32_t)(pw[p] * bytes))
+            return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display: stride[%d] smaller than a row", p);
+    int32_t dstride[3];
+    size_t off[3], ptotal;
+    device_plane_layout(w, h, profile, dstride, off, &ptotal);
+    const size_t dpitch = ((size_t)w * 4 + 255) & ~(size_t)255;
+    if ((rc = reserve(ctx, ctx->d_planes, ptotal)) || (rc = reserve(ctx, ctx->d_aux, dpitch * h)))
+        return rc;
+    uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
+                      (uint8_t *)ctx->d_planes.p + off[2]};
+    for (int p = 0; p < 3; p++)
+        CU_TRY(ctx, cudaMemcpy2DAsync(dp[p], (size_t)dstride[p], planes[p], (size_t)strides[p], (size_t)pw[p] * bytes, ph[p],
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    rc = lumacu_display_dev(ctx, dp, dstride, w, h, profile, pre_scaling, params, (uint8_t *)ctx->d_aux.p, (int32_t)dpitch, 1,
+                            nullptr, 0, ctx->stream);
+    if (rc)
+        return rc;
+    CU_TRY(ctx, cudaMemcpy2DAsync(rgba, (size_t)rgba_pitch, ctx->d_aux.p, dpitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LUMACU_OK;
 }
 

@@ -395,3 +395,19 @@ class LumaDecoder:
         check(q._lib.lumacu_decode(hnd, ptrs, strides, w, h, profile, float(self.m_params.preScaling),
                                    self.m_frame.ctypes.data), hnd, "lumacu_decode")
         return self.m_frame
+
+    def display(self, planes, w: int, h: int, exposure: float = 1.0, gamma: float = 2.2, user_scaling: float = 1.0,
+                do_tmo: bool = False, ldr_sim: bool = False, profile: int | None = None) -> np.ndarray:
+        """The player's display path (src/lumaplay_dequantizer.frag:70-157): planes -> 8-bit RGBA [h, w, 4]."""
+        if not self.m_initialized:
+            raise LumaException("LumaDecoder: not initialized", 3)
+        profile = self.m_params.profile if profile is None else int(profile)
+        q = self.m_quant
+        q._upload()
+        ptrs, strides = _plane_args(planes)
+        out = np.empty((h, w, 4), dtype=np.uint8)
+        p = _lib.DisplayParams(float(exposure), float(gamma), float(user_scaling), int(do_tmo), int(ldr_sim))
+        hnd = q.ctx.handle
+        check(q._lib.lumacu_display(hnd, ptrs, strides, w, h, profile, float(self.m_params.preScaling), C.byref(p),
+                                    out.ctypes.data, w * 4), hnd, "lumacu_display")
+        return out
