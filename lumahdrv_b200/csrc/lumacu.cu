@@ -632,34 +632,46 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
      * the 1e8 bucket by an unsigned min on the device, which needs every threshold to be <= 1e8.  The table starts
      * one bucket below 1e-4 because a 2x2 mean of four 1e-4 samples may round an ulp below 1e-4. */
     std::vector<uint32_t> dtab;
-    uint32_t d_shift = 0, d_lo = 0;
+    uint32_t d_shift = 0, d_lo = 0, d_lo_key = 0, d_hi_key = 0;
     if (mode == SEARCH_BUCKET && thr[0] > 0x80000000u && max_val <= 32767u) {
         const uint32_t k_lo = f2u(1e-4f), k_hi = f2u(1e8f);
-        if ((thr[max_val - 1] ^ 0x80000000u) <= k_hi) {
-            for (uint32_t S = 16; S >= 12 && dtab.empty(); S--) {
-                const uint32_t lo = (k_lo >> S) - 1u, n = (k_hi >> S) - lo + 1u;
-                if ((size_t)n * 4 > 48 * 1024)
-                    break;
-                bool ok = true;
-                for (uint32_t j = 1; j < max_val && ok; j++)
-                    ok = ((thr[j] ^ 0x80000000u) >> S) != ((thr[j - 1] ^ 0x80000000u) >> S);
-                if (!ok)
-                    continue;
-                dtab.resize(n);
-                uint32_t j = 0; /* thresholds below the current bucket */
-                for (uint32_t b = 0; b < n; b++) {
-                    const uint32_t kb = lo + b;
-                    while (j < max_val && ((thr[j] ^ 0x80000000u) >> S) < kb)
-                        j++;
-                    uint32_t thr_low = 1u << S;
-                    if (j < max_val && ((thr[j] ^ 0x80000000u) >> S) == kb)
-                        thr_low = (thr[j] ^ 0x80000000u) - (kb << S);
-                    dtab[b] = (j << 16) + 0x10000u - thr_low - (kb << S);
-                }
-                d_shift = S;
-                d_lo = lo;
-                dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u); /* the kernels stage it with 128-bit loads */
+        const uint32_t t_first = thr[0] ^ 0x80000000u, t_last = thr[max_val - 1] ^ 0x80000000u;
+        for (uint32_t S = 16; S >= 12 && dtab.empty(); S--) {
+            bool ok = true;
+            for (uint32_t j = 1; j < max_val && ok; j++)
+                ok = ((thr[j] ^ 0x80000000u) >> S) != ((thr[j - 1] ^ 0x80000000u) >> S);
+            if (!ok)
+                continue; /* two thresholds share a bucket: finer buckets */
+            /* (A) the whole clamp range [1e-4, 1e8] (one bucket more below: a 2x2 mean of four 1e-4 samples may round
+             *     an ulp below 1e-4): the device only needs the upper clamp;
+             * (B) just the thresholds' own range plus a bucket either side: smaller, needs both clamps on the device
+             *     (LUTs such as LOG-12 whose buckets are too fine for (A) to fit in shared memory). */
+            uint32_t lo = (k_lo >> S) - 1u, hi = k_hi >> S;
+            bool clamp_lo = false;
+            if (t_last > k_hi || (size_t)(hi - lo + 1u) * 4 > 48 * 1024) {
+                lo = (t_first >> S) - 1u;
+                hi = (t_last >> S) + 1u;
+                clamp_lo = true;
+                if ((size_t)(hi - lo + 1u) * 4 > 48 * 1024)
+                    break; /* finer buckets only get bigger */
             }
+            const uint32_t n = hi - lo + 1u;
+            dtab.resize(n);
+            uint32_t j = 0; /* thresholds below the current bucket */
+            for (uint32_t b = 0; b < n; b++) {
+                const uint32_t kb = lo + b;
+                while (j < max_val && ((thr[j] ^ 0x80000000u) >> S) < kb)
+                    j++;
+                uint32_t thr_low = 1u << S;
+                if (j < max_val && ((thr[j] ^ 0x80000000u) >> S) == kb)
+                    thr_low = (thr[j] ^ 0x80000000u) - (kb << S);
+                dtab[b] = (j << 16) + 0x10000u - thr_low - (kb << S);
+            }
+            d_shift = S;
+            d_lo = lo;
+            d_lo_key = clamp_lo ? (lo << S) : 0u;
+            d_hi_key = clamp_lo ? (((hi + 1u) << S) - 1u) : k_hi;
+            dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u); /* the kernels stage it with 128-bit loads */
         }
     }
 
@@ -710,6 +722,8 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
     q.d_shift = d_shift;
     q.d_lo = d_lo;
     q.d_n = (uint32_t)dtab.size();
+    q.d_lo_key = d_lo_key;
+    q.d_hi_key = d_hi_key;
     q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
     q.max_val = max_val;
     q.max_val_color = max_val_color;
@@ -1006,7 +1020,8 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
             variant = kEncVariantPlain;
         /* walk 0 = direct search table (one LDS per sample); otherwise bucket heads + <= walk threshold compares */
         const bool direct = ctx->q.dtab && (ctx->color_space == CS_LUV || ctx->color_space == CS_XYZ) && !ctx->no_direct;
-        int walk = direct ? 0 : (int)ctx->q.walk;
+        const int walk_direct = ctx->q.d_lo_key ? -1 : 0; /* -1: direct table that needs the lower clamp too */
+        int walk = direct ? walk_direct : (int)ctx->q.walk;
         fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
         if (!fn && direct) { /* tuning variants exist for one search flavour only */
             walk = (int)ctx->q.walk;
@@ -1014,10 +1029,10 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
         }
         if (!fn && variant != kEncVariantPlain) {
             variant = kEncVariantPlain;
-            walk = direct ? 0 : (int)ctx->q.walk;
+            walk = direct ? walk_direct : (int)ctx->q.walk;
             fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
         }
-        if (fn && walk == 0)
+        if (fn && walk <= 0)
             smem = (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
         if (fn && staged && variant != kEncVariantPlain)
             smem += kEncStagedSmemBytes;

@@ -106,3 +106,33 @@ def test_luma_codes_are_fixed_points(lumalib, torch_cuda):
         q = L.LumaQuantizer().setQuantizer(ptf, bits, "LUV", 8)
         codes = np.arange(1 << bits, dtype=np.float32)
         assert np.array_equal(q.quantize(q.dequantize(codes, 0), 0), codes), (ptf, bits)
+
+
+@pytest.mark.parametrize("w,h", [(1280, 720), (1920, 1080)])
+def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w, h):
+    """lumacu_set_tuning: pipelining / occupancy / search variants of the tuned kernels (register prefetch, tensor-map
+    TMA staging, bucket search, block sizing) are performance knobs only."""
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+
+    t = DeviceTransform(0)
+    n = 3
+    rgb = torch.stack([torch.from_numpy(po.noise_frame(w, h, seed=300 + i)) for i in range(n)]).cuda()
+    rgb[1, :, 3, 5] = float("nan")
+    ctx = t.quant.ctx
+    ctx.set_tuning(0, 0, 0)
+    ref_planes = [p.clone() for p in t.encode(rgb)]
+    ref_out = t.decode(ref_planes, w, h).clone()
+    o = po.Oracle().setQuantizer("PQ", 11, "LUV", 8)
+    cpu_planes, _ = o.encode(rgb[0].cpu().numpy().copy(), 2, 1.0)
+    for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
+        assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
+    for enc_v, dec_v, cap in [(3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
+                              (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
+        ctx.set_tuning(enc_v, dec_v, cap)
+        planes = t.encode(rgb)
+        for a, b in zip(planes, ref_planes):
+            assert torch.equal(a, b), f"encode variant {enc_v} cap {cap}"
+        out = t.decode(ref_planes, w, h)
+        assert torch.equal(out.view(torch.int32), ref_out.view(torch.int32)), f"decode variant {dec_v} cap {cap}"
+    ctx.set_tuning(0, 0, 0)
