@@ -21,6 +21,7 @@
 
 #include "exr_interface.h"
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,11 @@ static uint32_t fnv(const void *p, size_t n, uint32_t h = 2166136261u)
         h *= 16777619u;
     }
     return h;
+}
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static uint64_t g_state;
@@ -106,7 +112,9 @@ int main(int argc, char **argv)
             printf("in %d %08x\n", f, fnv(frame.buffer, (size_t)3 * w * h * sizeof(float)));
             if (!encoder.initialized())
                 encoder.initialize(file, frame.width, frame.height);
+            const double t0 = now_ms();
             encoder.encode(&frame);
+            fprintf(stderr, "time encode %d %.3f ms\n", f, now_ms() - t0); /* stderr: stdout must stay comparable */
         }
         encoder.finish();
 
@@ -122,9 +130,11 @@ int main(int argc, char **argv)
 
         LumaDecoder decoder(file);
         for (int f = 0;; f++) {
+            const double t0 = now_ms();
             LumaFrame *frame = decoder.decode();
             if (frame == NULL)
                 break;
+            fprintf(stderr, "time decode %d %.3f ms\n", f, now_ms() - t0);
             LumaDecoderParams dp = decoder.getParams();
             unsigned char **planes = decoder.getBuffer();
             uint32_t ph[3];
