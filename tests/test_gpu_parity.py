@@ -318,6 +318,29 @@ def test_mean_luminance_warning(L, po):
     assert not enc.warnings
 
 
+def test_ycbcr_powf_dense(L, po):
+    """The device restatement of glibc's powf against the host libm, through LumaQuantizer::transformColorSpace for
+    CS_YCBCR (8 powf per pixel forward, 8 inverse): 2 Mpixel of log-uniform values over 18 decades plus specials."""
+    w, h = 2048, 1024
+    rng = np.random.default_rng(11)
+    frame = np.power(np.float32(10.0), rng.uniform(-12.0, 6.0, size=(3, h, w)).astype(np.float32)).astype(np.float32)
+    frame[:, 0, :8] = np.array([0.0, -1.0, np.inf, np.nan, 1e-45, 1e-38, 1e4, 1e-10], dtype=np.float32)
+    for lmax, sc in ((1e4, 1.0), (1000.0, 20.0)):
+        q = L.LumaQuantizer()
+        q.setQuantizer("PQ", 10, "YCBCR", 10, lmax, 0.01)
+        o = po.Oracle().setQuantizer("PQ", 10, "YCBCR", 10, lmax, 0.01)
+        fwd_gpu, fwd_cpu = frame.copy(), frame.copy()
+        assert q.transformColorSpace(fwd_gpu, True, sc)
+        assert o.transformColorSpace(fwd_cpu, True, sc)
+        assert bits_equal(fwd_gpu, fwd_cpu), f"forward, max ulp {max_ulp(fwd_gpu, fwd_cpu)}"
+        # inverse on a plausible transformed frame: luminance plane + two chroma planes in [0, 1]
+        inv = np.stack([np.abs(frame[0]), rng.random((h, w), dtype=np.float32), rng.random((h, w), dtype=np.float32)])
+        inv_gpu, inv_cpu = inv.copy(), inv.copy()
+        assert q.transformColorSpace(inv_gpu, False, sc)
+        assert o.transformColorSpace(inv_cpu, False, sc)
+        assert bits_equal(inv_gpu, inv_cpu), f"inverse, max ulp {max_ulp(inv_gpu, inv_cpu)}"
+
+
 def test_zz_both_kernel_families_were_exercised(L):
     """Runs last in this module: the parity cases above must have hit the tuned AND the generic kernels."""
     if not KERNEL_PATHS_SEEN:
