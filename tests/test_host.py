@@ -117,3 +117,25 @@ def test_frame_shards():
             assert sum(len(g) for g in got) == n
             assert sorted(i for g in got for i in g) == list(range(n))
             assert max(len(g) for g in got) - min(len(g) for g in got) <= 1
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's own CPU code, oracle/_ref) prints ONE JSON line with the keys the
+    driver reads; the CUDA arm's config/metric/unit are the same strings."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpixels/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("Mpixels/s encode+decode") and "3840x2160" in d["config"]["workload"]
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
