@@ -276,6 +276,24 @@ def ours_arm(args):
     px_step = F * W * H  # per GPU
     value = world * px_step * args.steps / (total_ms / 1e3) / 1e6
 
+    # context for the roofline fraction: a plain device-to-device copy on THIS lease, measured the way
+    # MEASURED_PEAKS.json was (torch copy_ over 1 GiB, read + write bytes, best of 10, CUDA events)
+    copy_gbs = None
+    if rank == 0:
+        src_c = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        dst_c = torch.empty_like(src_c)
+        best = float("inf")
+        for i in range(12):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            dst_c.copy_(src_c)
+            c1.record()
+            c1.synchronize()
+            if i >= 2:
+                best = min(best, c0.elapsed_time(c1))
+        copy_gbs = 2 * (1 << 30) / (best / 1e3) / 1e9
+        del src_c, dst_c
+
     # sanity: the timed work really produced the round trip (compare one frame with the input scale)
     st = t.stats_to_numpy(stats)
     assert np.all(np.isfinite(st["sum"])) and np.all(st["sum"] > 0)
@@ -411,7 +429,8 @@ def ours_arm(args):
                          "encode_ms": enc_ms, "decode_ms": dec_ms,
                          "encode_gbs": bytes_pass / (enc_ms / 1e3) / 1e9, "decode_gbs": bytes_pass / (dec_ms / 1e3) / 1e9,
                          "round_trip_frac_of_peak": (2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9) / peak,
-                         "frac_of_nominal_8tbs": (2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9) / 8000.0},
+                         "frac_of_nominal_8tbs": (2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9) / 8000.0,
+                         "copy_gbs_this_lease": copy_gbs},
             "gpu_launches": launches,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
