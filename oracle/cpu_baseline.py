@@ -31,7 +31,7 @@ def _worker(args):
     if use_ref:
         impl = po.Reference(ptf=q["ptf"], ptfBitDepth=q["ptfBitDepth"], colorSpace=q["colorSpace"],
                             colorBitDepth=q["colorBitDepth"], profile=q["profile"], bitDepth=q["bitDepth"],
-                            preScaling=q["preScaling"], maxLum=q["maxLum"], minLum=q["minLum"])
+                            preScaling=q["preScaling"], maxLum=q["maxLum"], minLum=q["minLum"], o0=cfg.get("o0", False))
     else:
         impl = po.Oracle().setQuantizer(q["ptf"], q["ptfBitDepth"], q["colorSpace"], q["colorBitDepth"], q["maxLum"],
                                         q["minLum"])
@@ -57,8 +57,8 @@ def _worker(args):
     return {"enc_s": t_enc, "dec_s": t_dec, "kind": "reference" if use_ref else "port"}
 
 
-def run(workers: int, frames: int, width: int, height: int, quant: dict, force_port: bool = False) -> dict:
-    cfg = {"width": width, "height": height, "frames": frames, "quant": quant, "force_port": force_port}
+def run(workers: int, frames: int, width: int, height: int, quant: dict, force_port: bool = False, o0: bool = False) -> dict:
+    cfg = {"width": width, "height": height, "frames": frames, "quant": quant, "force_port": force_port, "o0": o0}
     t0 = time.perf_counter()
     if workers == 1:
         res = [_worker((0, cfg))]
@@ -74,7 +74,9 @@ def run(workers: int, frames: int, width: int, height: int, quant: dict, force_p
         "cores": workers,
         "kind": res[0]["kind"],
         "sample": f"{workers} worker(s) x {frames} frame(s) {width}x{height} round trip (encode+decode), "
-                  f"{'libluma_ref.so -O2 (bit-identical to the reference -O0 build)' if res[0]['kind'] == 'reference' else 'C restatement -O2'}",
+                  + (("libluma_ref_O0.so (-O0, the reference's own CMake default)" if o0 else
+                      "libluma_ref.so -O2 (bit-identical to the reference -O0 build)") if res[0]["kind"] == "reference"
+                     else "C restatement -O2"),
         "per_core_mpx_s": px / (sum(r["enc_s"] + r["dec_s"] for r in res) / len(res)) / 1e6,
         "encode_mpx_s_per_core": px / (sum(r["enc_s"] for r in res) / len(res)) / 1e6,
         "decode_mpx_s_per_core": px / (sum(r["dec_s"] for r in res) / len(res)) / 1e6,
@@ -93,6 +95,7 @@ if __name__ == "__main__":
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--port", action="store_true")
+    ap.add_argument("--o0", action="store_true", help="time the -O0 build of the reference (its CMake default)")
     a = ap.parse_args()
     n = a.workers or len(os.sched_getaffinity(0))
-    print(json.dumps(run(n, a.frames, a.width, a.height, DEFAULT_QUANT, a.port)))
+    print(json.dumps(run(n, a.frames, a.width, a.height, DEFAULT_QUANT, a.port, a.o0)))
