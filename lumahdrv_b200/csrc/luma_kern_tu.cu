@@ -113,12 +113,12 @@ static enc_fn pick_walk(int walk)
 #if LUMA_TU_CS == 0 || LUMA_TU_CS == 3
     if (walk == 0) /* direct search table over [1e-4, 1e8] (positive searched values: Lu'v' Y, XYZ) */
         return encode_fast_kernel<kCS, SUB, BYTES, 0, PF, 4>;
-    if (walk == -1) /* direct search table over the thresholds' own range (lower clamp on the device as well) */
-        return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4>;
 #else
-    if (walk <= 0)
+    if (walk == 0)
         return nullptr;
 #endif
+    if (walk == -1) /* direct search table over the thresholds' own range (both clamps on the device) */
+        return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4>;
 #if LUMA_TU_CS == 0
     /* the headline colour space gets the exact walk length */
     if (walk <= 1)

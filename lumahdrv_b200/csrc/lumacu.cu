@@ -633,22 +633,27 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
      * one bucket below 1e-4 because a 2x2 mean of four 1e-4 samples may round an ulp below 1e-4. */
     std::vector<uint32_t> dtab;
     uint32_t d_shift = 0, d_lo = 0, d_lo_key = 0, d_hi_key = 0;
+    /* key space of the table: raw float bits where the searched values are positive (Lu'v' Y, XYZ), otherwise the
+     * ordered keys the thresholds are already stored in (RGB, YCbCr luminance: any sign, any NaN) */
+    const bool raw_keys = (color_space == CS_LUV || color_space == CS_XYZ);
+    const uint32_t flip = raw_keys ? 0x80000000u : 0u;
     if (mode == SEARCH_BUCKET && thr[0] > 0x80000000u && max_val <= 32767u) {
         const uint32_t k_lo = f2u(1e-4f), k_hi = f2u(1e8f);
-        const uint32_t t_first = thr[0] ^ 0x80000000u, t_last = thr[max_val - 1] ^ 0x80000000u;
+        const uint32_t t_first = thr[0] ^ flip, t_last = thr[max_val - 1] ^ flip;
         for (uint32_t S = 16; S >= 12 && dtab.empty(); S--) {
             bool ok = true;
             for (uint32_t j = 1; j < max_val && ok; j++)
-                ok = ((thr[j] ^ 0x80000000u) >> S) != ((thr[j - 1] ^ 0x80000000u) >> S);
+                ok = ((thr[j] ^ flip) >> S) != ((thr[j - 1] ^ flip) >> S);
             if (!ok)
                 continue; /* two thresholds share a bucket: finer buckets */
-            /* (A) the whole clamp range [1e-4, 1e8] (one bucket more below: a 2x2 mean of four 1e-4 samples may round
-             *     an ulp below 1e-4): the device only needs the upper clamp;
+            /* (A) raw keys only: the whole clamp range [1e-4, 1e8] (one bucket more below: a 2x2 mean of four 1e-4
+             *     samples may round an ulp below 1e-4): the device only needs the upper clamp;
              * (B) just the thresholds' own range plus a bucket either side: smaller, needs both clamps on the device
-             *     (LUTs such as LOG-12 whose buckets are too fine for (A) to fit in shared memory). */
+             *     (LUTs such as LOG-12 whose buckets are too fine for (A) to fit in shared memory, and every
+             *     ordered-key table). */
             uint32_t lo = (k_lo >> S) - 1u, hi = k_hi >> S;
             bool clamp_lo = false;
-            if (t_last > k_hi || (size_t)(hi - lo + 1u) * 4 > 48 * 1024) {
+            if (!raw_keys || t_last > k_hi || (size_t)(hi - lo + 1u) * 4 > 48 * 1024) {
                 lo = (t_first >> S) - 1u;
                 hi = (t_last >> S) + 1u;
                 clamp_lo = true;
@@ -660,11 +665,11 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
             uint32_t j = 0; /* thresholds below the current bucket */
             for (uint32_t b = 0; b < n; b++) {
                 const uint32_t kb = lo + b;
-                while (j < max_val && ((thr[j] ^ 0x80000000u) >> S) < kb)
+                while (j < max_val && ((thr[j] ^ flip) >> S) < kb)
                     j++;
                 uint32_t thr_low = 1u << S;
-                if (j < max_val && ((thr[j] ^ 0x80000000u) >> S) == kb)
-                    thr_low = (thr[j] ^ 0x80000000u) - (kb << S);
+                if (j < max_val && ((thr[j] ^ flip) >> S) == kb)
+                    thr_low = (thr[j] ^ flip) - (kb << S);
                 dtab[b] = (j << 16) + 0x10000u - thr_low - (kb << S);
             }
             d_shift = S;
@@ -1019,7 +1024,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
             make_rgb_tensor_map(ctx, d_rgb, w, h, a.rgb_plane_stride, a.rgb_frame_stride, n_frames, a.rgb_tmap) != LUMACU_OK)
             variant = kEncVariantPlain;
         /* walk 0 = direct search table (one LDS per sample); otherwise bucket heads + <= walk threshold compares */
-        const bool direct = ctx->q.dtab && (ctx->color_space == CS_LUV || ctx->color_space == CS_XYZ) && !ctx->no_direct;
+        const bool direct = ctx->q.dtab && !ctx->no_direct;
         const int walk_direct = ctx->q.d_lo_key ? -1 : 0; /* -1: direct table that needs the lower clamp too */
         int walk = direct ? walk_direct : (int)ctx->q.walk;
         fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
