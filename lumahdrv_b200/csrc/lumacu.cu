@@ -69,6 +69,17 @@ struct DeviceBuffer {
     size_t cap = 0;
 };
 
+/* What the internal launchers need beyond the public *_dev signatures. */
+struct LaunchOpts {
+    bool passthrough = false;      /* skip the colour transform: LumaEncoder::setChannels / LumaDecoder::getVpxChannels halves */
+    size_t rgb_plane_stride = 0;   /* floats between the R, G, B planes (0 = w*h): row bands of a larger frame */
+    /* display launch (decode only): tone curve + gamma -> 8-bit RGBA instead of the float frame */
+    const lumacu_display_params *display = nullptr;
+    uint8_t *rgba = nullptr;
+    int32_t rgba_pitch = 0;
+    size_t rgba_frame_stride = 0;
+};
+
 } // namespace
 
 struct lumacu_ctx {
@@ -80,11 +91,6 @@ struct lumacu_ctx {
     std::unordered_map<const void *, std::pair<size_t, int>> occupancy; /* kernel -> (smem, blocks per SM) */
     bool force_generic = false; /* tests: run the literal kernels */
     bool last_fast = false;     /* the last encode/decode launch used a tuned kernel */
-    bool passthrough = false;   /* next encode/decode launch skips the colour transform (set by *_planes) */
-    const lumacu_display_params *display = nullptr; /* next decode launch is a display launch (set by lumacu_display_dev) */
-    uint8_t *display_rgba = nullptr;
-    int32_t display_pitch = 0;
-    size_t display_frame_stride = 0;
     int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
     int grid_tpt = 0;                     /* tuning sweep: tiles per thread of a multi-frame launch (0 = default) */
@@ -107,7 +113,6 @@ struct lumacu_ctx {
     DeviceBuffer d_rgb, d_planes, d_stats, d_aux;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
-    size_t plane_stride_override = 0; /* floats between the R,G,B planes of the NEXT *_dev launch (0 = w*h): band launches */
     int host_bands = 0;               /* tuning: number of row bands per host-pointer call (0 = automatic) */
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -960,10 +965,10 @@ int check_profile(lumacu_ctx *ctx, int profile, uint32_t w, uint32_t h, bool enc
 
 } // namespace
 
-extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, uint32_t w, uint32_t h,
-                                 int profile, float pre_scaling, uint8_t *const d_planes[3], const int32_t strides[3],
-                                 uint32_t n_frames, size_t rgb_frame_stride, const size_t plane_frame_stride[3],
-                                 lumacu_frame_stats *d_stats, void *stream)
+static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, uint32_t w, uint32_t h, int profile,
+                         float pre_scaling, uint8_t *const d_planes[3], const int32_t strides[3], uint32_t n_frames,
+                         size_t rgb_frame_stride, const size_t plane_frame_stride[3], lumacu_frame_stats *d_stats, void *stream,
+                         const LaunchOpts &opt)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
@@ -992,7 +997,7 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     a.q = ctx->q;
     a.rgb = d_rgb;
     a.rgb_out = d_rgb_out;
-    a.rgb_plane_stride = ctx->plane_stride_override ? ctx->plane_stride_override : (size_t)w * h;
+    a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
     a.out_plane_stride = a.rgb_plane_stride;
     a.out_frame_stride = a.rgb_frame_stride;
@@ -1012,9 +1017,9 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     }
     enc_fn fn = nullptr;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
-    a.passthrough = ctx->passthrough ? 1 : 0;
+    a.passthrough = opt.passthrough ? 1 : 0;
     size_t smem = ctx->smem_enc;
-    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic && !ctx->passthrough) {
+    if (vec && small32 && !d_rgb_out && ctx->fast_enc_ok && !ctx->force_generic && !opt.passthrough) {
         int variant = ctx->enc_variant ? ctx->enc_variant : kEncDefaultVariant;
         const int pf = variant / 10;
         const bool staged = (pf == 8);
@@ -1070,15 +1075,24 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
     return LUMACU_OK;
 }
 
-extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
-                                 uint32_t h, int profile, float pre_scaling, float *d_rgb, uint32_t n_frames,
-                                 size_t rgb_frame_stride, const size_t plane_frame_stride[3], void *stream)
+extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, uint32_t w, uint32_t h,
+                                 int profile, float pre_scaling, uint8_t *const d_planes[3], const int32_t strides[3],
+                                 uint32_t n_frames, size_t rgb_frame_stride, const size_t plane_frame_stride[3],
+                                 lumacu_frame_stats *d_stats, void *stream)
+{
+    return encode_launch(ctx, d_rgb, d_rgb_out, w, h, profile, pre_scaling, d_planes, strides, n_frames, rgb_frame_stride,
+                         plane_frame_stride, d_stats, stream, LaunchOpts());
+}
+
+static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
+                         int profile, float pre_scaling, float *d_rgb, uint32_t n_frames, size_t rgb_frame_stride,
+                         const size_t plane_frame_stride[3], void *stream, const LaunchOpts &opt)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
         return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_decode_dev: lumacu_set_quantizer has not been called");
-    if (!d_rgb || !d_planes || !strides || !d_planes[0] || !d_planes[1] || !d_planes[2])
+    if ((!d_rgb && !opt.display) || !d_planes || !strides || !d_planes[0] || !d_planes[1] || !d_planes[2])
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_dev: NULL pointer argument");
     int rc = check_profile(ctx, profile, w, h, false);
     if (rc)
@@ -1100,7 +1114,7 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     DecArgs a{};
     a.q = ctx->q;
     a.rgb = d_rgb;
-    a.rgb_plane_stride = ctx->plane_stride_override ? ctx->plane_stride_override : (size_t)w * h;
+    a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
     a.w = w;
     a.h = h;
@@ -1118,16 +1132,16 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     dec_fn fn = nullptr;
     size_t smem = ctx->smem_dec;
     const bool small32 = (uint64_t)w * h * 4 < (1ull << 32) && (uint64_t)strides[0] * h < (1ull << 32);
-    a.passthrough = ctx->passthrough ? 1 : 0;
-    if (ctx->display) {
-        a.rgba = ctx->display_rgba;
-        a.rgba_pitch = ctx->display_pitch;
-        a.rgba_frame_stride = ctx->display_frame_stride;
-        a.disp_exposure = ctx->display->exposure;
-        a.disp_scaling = pre_scaling / ctx->display->user_scaling; /* lumaplay.cpp:406 */
-        a.disp_inv_gamma = 1.0f / ctx->display->gamma;
-        a.disp_tmo = ctx->display->do_tmo ? 1 : 0;
-        a.disp_ldr = ctx->display->ldr_sim ? 1 : 0;
+    a.passthrough = opt.passthrough ? 1 : 0;
+    if (opt.display) {
+        a.rgba = opt.rgba;
+        a.rgba_pitch = opt.rgba_pitch;
+        a.rgba_frame_stride = opt.rgba_frame_stride;
+        a.disp_exposure = opt.display->exposure;
+        a.disp_scaling = pre_scaling / opt.display->user_scaling; /* lumaplay.cpp:406 */
+        a.disp_inv_gamma = 1.0f / opt.display->gamma;
+        a.disp_tmo = opt.display->do_tmo ? 1 : 0;
+        a.disp_ldr = opt.display->ldr_sim ? 1 : 0;
         a.prescale = 0; /* the player folds preScaling into `scaling` instead of dividing the frame */
         vec = (w % 4 == 0);
         for (int p = 0; p < 3; p++) {
@@ -1136,7 +1150,7 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
         }
         vec = vec && aligned(a.rgba, 16) && (a.rgba_frame_stride % 16 == 0);
     }
-    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !ctx->passthrough && !ctx->display) {
+    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !opt.passthrough && !opt.display) {
         fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
         if (!fn)
             fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
@@ -1156,6 +1170,14 @@ extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[
     return LUMACU_OK;
 }
 
+extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
+                                 uint32_t h, int profile, float pre_scaling, float *d_rgb, uint32_t n_frames,
+                                 size_t rgb_frame_stride, const size_t plane_frame_stride[3], void *stream)
+{
+    return decode_launch(ctx, d_planes, strides, w, h, profile, pre_scaling, d_rgb, n_frames, rgb_frame_stride, plane_frame_stride,
+                         stream, LaunchOpts());
+}
+
 /* ---- display decode ------------------------------------------------------------------- */
 extern "C" int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
                                   uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
@@ -1172,15 +1194,12 @@ extern "C" int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: gamma and user_scaling must be positive");
     if (!aligned(d_rgba, 4))
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: rgba must be 4-byte aligned");
-    ctx->display = params;
-    ctx->display_rgba = d_rgba;
-    ctx->display_pitch = rgba_pitch;
-    ctx->display_frame_stride = rgba_frame_stride ? rgba_frame_stride : (size_t)rgba_pitch * h;
-    /* d_rgb is unused in display mode; pass the output buffer to satisfy the NULL check */
-    const int rc = lumacu_decode_dev(ctx, d_planes, strides, w, h, profile, pre_scaling, reinterpret_cast<float *>(d_rgba), n_frames,
-                                     0, plane_frame_stride, stream);
-    ctx->display = nullptr;
-    return rc;
+    LaunchOpts opt;
+    opt.display = params;
+    opt.rgba = d_rgba;
+    opt.rgba_pitch = rgba_pitch;
+    opt.rgba_frame_stride = rgba_frame_stride ? rgba_frame_stride : (size_t)rgba_pitch * h;
+    return decode_launch(ctx, d_planes, strides, w, h, profile, pre_scaling, nullptr, n_frames, 0, plane_frame_stride, stream, opt);
 }
 
 /* ---- frame sources on the device ------------------------------------------------------------------------ */
@@ -1357,9 +1376,9 @@ inline uint32_t band_row(uint32_t h, int nb, int b) /* first row of band b; even
 
 } // namespace
 
-extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
-                             uint8_t *const planes[3], const int32_t strides[3], int write_back,
-                             lumacu_frame_stats *stats)
+static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
+                       uint8_t *const planes[3], const int32_t strides[3], int write_back, lumacu_frame_stats *stats,
+                       bool passthrough)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
@@ -1390,6 +1409,9 @@ extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h
     uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
                       (uint8_t *)ctx->d_planes.p + off[2]};
     lumacu_frame_stats *d_stats = (lumacu_frame_stats *)ctx->d_stats.p;
+    LaunchOpts opt;
+    opt.passthrough = passthrough;
+    opt.rgb_plane_stride = npx; /* a band's planes are still a whole frame apart */
     for (int b = 0; b < nb; b++) {
         const uint32_t y0 = band_row(h, nb, b), y1 = band_row(h, nb, b + 1), rows = y1 - y0;
         /* the band's rows of the three planes in one strided copy (pitch = one plane) */
@@ -1400,10 +1422,8 @@ extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h
         const uint32_t cy0 = sub ? y0 >> 1 : y0;
         uint8_t *bp[3] = {dp[0] + (size_t)y0 * dstride[0], dp[1] + (size_t)cy0 * dstride[1], dp[2] + (size_t)cy0 * dstride[2]};
         float *band = d_rgb + (size_t)y0 * w;
-        ctx->plane_stride_override = npx;
-        rc = lumacu_encode_dev(ctx, band, write_back ? band : nullptr, w, rows, profile, pre_scaling, bp, dstride, 1, 0, nullptr,
-                               stats ? d_stats + b : nullptr, ctx->stream);
-        ctx->plane_stride_override = 0;
+        rc = encode_launch(ctx, band, write_back ? band : nullptr, w, rows, profile, pre_scaling, bp, dstride, 1, 0, nullptr,
+                           stats ? d_stats + b : nullptr, ctx->stream, opt);
         if (rc)
             return rc;
         CU_TRY(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
@@ -1432,8 +1452,15 @@ extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h
     return LUMACU_OK;
 }
 
-extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
-                             uint32_t h, int profile, float pre_scaling, float *rgb)
+extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
+                             uint8_t *const planes[3], const int32_t strides[3], int write_back,
+                             lumacu_frame_stats *stats)
+{
+    return host_encode(ctx, rgb, w, h, profile, pre_scaling, planes, strides, write_back, stats, false);
+}
+
+static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
+                       int profile, float pre_scaling, float *rgb, bool passthrough)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
@@ -1463,6 +1490,9 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
     float *d_rgb = (float *)ctx->d_rgb.p;
     uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
                       (uint8_t *)ctx->d_planes.p + off[2]};
+    LaunchOpts opt;
+    opt.passthrough = passthrough;
+    opt.rgb_plane_stride = npx;
     for (int b = 0; b < nb; b++) {
         const uint32_t y0 = nb == 1 ? 0 : band_row(h, nb, b), y1 = nb == 1 ? h : band_row(h, nb, b + 1), rows = y1 - y0;
         const uint8_t *bp[3];
@@ -1475,9 +1505,7 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
         CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         float *band = d_rgb + (size_t)y0 * w;
-        ctx->plane_stride_override = npx;
-        rc = lumacu_decode_dev(ctx, bp, dstride, w, rows, profile, pre_scaling, band, 1, 0, nullptr, ctx->stream);
-        ctx->plane_stride_override = 0;
+        rc = decode_launch(ctx, bp, dstride, w, rows, profile, pre_scaling, band, 1, 0, nullptr, ctx->stream, opt);
         if (rc)
             return rc;
         CU_TRY(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
@@ -1487,6 +1515,12 @@ extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], co
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
     return LUMACU_OK;
+}
+
+extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                             uint32_t h, int profile, float pre_scaling, float *rgb)
+{
+    return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, rgb, false);
 }
 
 extern "C" int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
@@ -1535,10 +1569,7 @@ extern "C" int lumacu_quantize_planes(lumacu_ctx *ctx, const float *frame, uint3
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
-    ctx->passthrough = true;
-    const int rc = lumacu_encode(ctx, const_cast<float *>(frame), w, h, profile, 1.0f, planes, strides, 0, stats);
-    ctx->passthrough = false;
-    return rc;
+    return host_encode(ctx, const_cast<float *>(frame), w, h, profile, 1.0f, planes, strides, 0, stats, true);
 }
 
 extern "C" int lumacu_dequantize_planes(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
@@ -1546,10 +1577,7 @@ extern "C" int lumacu_dequantize_planes(lumacu_ctx *ctx, const uint8_t *const pl
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
-    ctx->passthrough = true;
-    const int rc = lumacu_decode(ctx, planes, strides, w, h, profile, 1.0f, frame);
-    ctx->passthrough = false;
-    return rc;
+    return host_decode(ctx, planes, strides, w, h, profile, 1.0f, frame, true);
 }
 
 extern "C" int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs, float sc)
