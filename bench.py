@@ -171,6 +171,23 @@ def measured_traffic(kind: str, px_per_launch: float):
     return best if best else (None, None)
 
 
+def bind_to_gpu_numa(index: int):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index` (no-op when unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def ours_arm(args):
     import numpy as np
     import torch
@@ -195,6 +212,11 @@ def ours_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_baseline(args.cpu_frames)
+
+    # ---- NUMA: keep this rank's host threads (and therefore its pinned buffers, first touch) next to its GPU
+    affinity = None
+    if os.environ.get("LUMA_BENCH_AFFINITY", "1") != "0":
+        affinity = bind_to_gpu_numa(local)
 
     # ---- quantizer: rank 0 builds the LUT with its libm, everyone receives it (the only collective)
     n_lut = 1 << QUANT["ptfBitDepth"]
@@ -433,6 +455,7 @@ def ours_arm(args):
                          "copy_gbs_this_lease": copy_gbs},
             "gpu_launches": launches,
             "clocks": clocks,
+            "host_cpus_bound": affinity,
             "wall_s_timed_region": t_wall,
         }
         if e2e:
