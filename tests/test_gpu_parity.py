@@ -318,6 +318,50 @@ def test_mean_luminance_warning(L, po):
     assert not enc.warnings
 
 
+@pytest.mark.parametrize("kind", ["log_uniform", "adjacent_floats", "negative_and_denormal", "above_1e8", "tiny_range"])
+@pytest.mark.parametrize("cs", ["LUV", "XYZ", "RGB"])
+def test_encode_with_arbitrary_luts(L, po, kind, cs):
+    """Every search flavour (direct table over [1e-4,1e8], direct table over the thresholds' range, bucket walk,
+    binary search, literal replica) behind the same encode call, on LUTs the shipped PTFs never produce: whatever
+    table the quantizer holds (e.g. overlaid from attachment 434), the planes equal the reference loop."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{kind}/{cs}".encode()))  # stable across processes (str hash is salted)
+    bits = 10
+    n = 1 << bits
+    if kind == "log_uniform":
+        cand = np.power(10.0, rng.uniform(-3, 5, 4 * n))
+    elif kind == "adjacent_floats":
+        base = rng.integers(0x3C000000, 0x46000000, size=n // 2).astype(np.uint32)
+        cand = np.concatenate([base + i for i in range(4)]).astype(np.uint32).view(np.float32).astype(np.float64)
+    elif kind == "negative_and_denormal":
+        cand = np.concatenate([-np.power(10.0, rng.uniform(-3, 3, 2 * n)), np.power(10.0, rng.uniform(-44, 3, 2 * n))])
+    elif kind == "above_1e8":
+        cand = np.power(10.0, rng.uniform(2, 12, 4 * n))
+    else:
+        cand = 1.0 + rng.uniform(0, 1e-3, 4 * n)
+    cand = np.unique(cand.astype(np.float32))
+    cand = cand[np.isfinite(cand)]
+    assert cand.size >= n
+    lut = np.ascontiguousarray(cand[np.sort(rng.choice(cand.size, n, replace=False))])
+    enc = L.LumaEncoder()
+    enc.setParams(L.LumaEncoderParams(ptf="LINEAR", ptfBitDepth=bits, colorSpace=cs, colorBitDepth=8, profile=2, bitDepth=12))
+    w, h = 256, 64
+    enc.initialize(None, w, h)
+    enc.m_quant.setMapping(lut)
+    o = po.Oracle().setQuantizer("LINEAR", bits, cs, 8)
+    o.setMapping(lut)
+    frame = adversarial_frame(w, h, lut=lut, seed=3)
+    ref_planes, _ = o.encode(frame.copy(), 2, 1.0)
+    for path in (0, 2, 1):
+        enc.m_quant.ctx.set_kernel_path(1 if path == 1 else 0)
+        enc.m_quant.ctx.set_tuning(1000 if path == 2 else 0)
+        planes = enc.encode(frame.copy(), L.alloc_planes(w, h, 2))
+        for p, (a, b, (pw, ph)) in enumerate(zip(planes, ref_planes, po.plane_dims(w, h, 2))):
+            assert np.array_equal(a[:ph, :pw * 2], b[:ph, :pw * 2]), f"{kind} {cs} path {path} plane {p}"
+    enc.m_quant.ctx.set_kernel_path(0)
+    enc.m_quant.ctx.set_tuning(0)
+
+
 def test_ycbcr_powf_dense(L, po):
     """The device restatement of glibc's powf against the host libm, through LumaQuantizer::transformColorSpace for
     CS_YCBCR (8 powf per pixel forward, 8 inverse): 2 Mpixel of log-uniform values over 18 decades plus specials."""

@@ -139,3 +139,61 @@ def test_bench_reference_arm_json_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def _ordered_key(v):
+    b = np.asarray(v, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    k = np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000)
+    return np.where(np.isnan(v), 0xFFFFFFFF, k).astype(np.uint64)
+
+
+def test_thresholds_equal_reference_search_on_arbitrary_monotone_luts(lumalib, po):
+    """The core claim behind the device search: for ANY finite strictly increasing LUT (not just the shipped PTFs --
+    the decoder overlays whatever attachment 434 holds), LumaQuantizer::quantize(val, 0) == number of derived
+    thresholds whose ordered key is <= key(val).  Random LUTs with wildly uneven spacing (neighbouring floats,
+    denormals, negative entries, huge gaps), probes at the LUT entries, their float neighbours, midpoints and
+    random values; checked against the oracle's bisect-then-nearest loop (src/luma_quantizer.cpp:219-235)."""
+    rng = np.random.default_rng(2024)
+    lib = lumalib.lib()
+    ran = 0
+    for trial in range(48):
+        bits = int(rng.choice([1, 2, 4, 8, 10]))
+        n, m = 1 << bits, 4 << bits
+        kind = trial % 4
+        if kind == 0:    # log-uniform positives over 30 decades
+            cand = np.power(10.0, rng.uniform(-20, 10, m)).astype(np.float32)
+        elif kind == 1:  # clusters of adjacent floats: differences of 1-3 ulp
+            base = rng.integers(0x3A000000, 0x4A000000, size=max(1, m // 8)).astype(np.uint32)
+            cand = np.concatenate([base + i * rng.integers(1, 4) for i in range(8)]).astype(np.uint32).view(np.float32)
+        elif kind == 2:  # spans negative, zero and positive, with denormals
+            cand = np.concatenate([-np.power(10.0, rng.uniform(-40, 3, m // 2)), [0.0],
+                                   np.power(10.0, rng.uniform(-44, 3, m - m // 2 - 1))]).astype(np.float32)
+        else:            # linear ramp with tiny jitter
+            cand = (np.linspace(0.0, 1000.0, m) + rng.uniform(0, 1e-3, m)).astype(np.float32)
+        cand = np.unique(cand[np.isfinite(cand)])  # strictly increasing after fp32 rounding (-0.0 and 0.0 collapse)
+        if cand.size < n:
+            continue
+        start = int(rng.integers(0, cand.size - n + 1))
+        lut = np.ascontiguousarray(cand[start:start + n] if kind == 1 else cand[np.sort(rng.choice(cand.size, n, replace=False))])
+        ran += 1
+        thr = np.empty(n - 1, dtype=np.uint32)
+        assert lib.lumacu_derive_thresholds(lut.ctypes.data, n, thr.ctypes.data) == 1, f"trial {trial}"
+        thr64 = thr.astype(np.uint64)
+        assert np.all(np.diff(thr64.astype(np.int64)) >= 0)
+        o = po.Oracle().setQuantizer("LINEAR", bits, "LUV", 8)
+        assert o.getSize() == n - 1
+        o.setMapping(lut)
+        ubits = lut.view(np.uint32)
+        nb_up = (ubits + np.where(lut >= 0, 1, -1).astype(np.int64)).astype(np.uint32).view(np.float32)
+        nb_dn = (ubits - np.where(lut > 0, 1, -1).astype(np.int64)).astype(np.uint32).view(np.float32)
+        mids = ((lut[:-1].astype(np.float64) + lut[1:].astype(np.float64)) / 2).astype(np.float32)
+        probes = np.concatenate([lut, nb_up, nb_dn, mids, (mids.view(np.uint32) + 1).view(np.float32),
+                                 (mids.view(np.uint32) - 1).view(np.float32), rng.choice(lut, 64) * np.float32(1.000001),
+                                 np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38], dtype=np.float32)])
+        probes = probes[: 1500]
+        want = np.array([o.quantize(float(v), 0) for v in probes])
+        keys = _ordered_key(probes)
+        got = np.searchsorted(thr64, keys, side="right")
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, f"trial {trial} kind {kind}: val {probes[bad[0]]!r} -> {got[bad[0]]} vs reference {want[bad[0]]}"
+    assert ran >= 40
