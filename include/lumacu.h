@@ -292,7 +292,7 @@ int lumacu_set_kernel_path(lumacu_ctx *ctx, int path);
 /* 1 if the last encode/decode launch on this context ran a tuned kernel, 0 if generic. */
 int lumacu_last_kernel_path(const lumacu_ctx *ctx);
 /* Host-pointer entry points cut a frame into row bands whose H2D copy, kernel and D2H copy overlap on three
- * streams (DESIGN.md "host staging").  0 = automatic (8 bands for frames >= 1 Mpixel, else 1). */
+ * streams (DESIGN.md "host staging").  0 = automatic (about one band per 8 MiB of frame, at most 8). */
 int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
 /* Tuning sweep: pick one of the extra instantiations of the headline tuned kernels
  * (variant = 10 * PF + MINB: PF 1 = next tile prefetched into registers, MINB = resident blocks per SM

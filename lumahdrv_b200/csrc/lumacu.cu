@@ -1349,10 +1349,11 @@ int band_count(const lumacu_ctx *ctx, uint32_t w, uint32_t h)
 {
     if (ctx->host_bands > 0)
         return std::max(1, std::min<int>(ctx->host_bands, (int)(h / 2)));
-    const size_t px = (size_t)w * h;
-    if (px < (size_t)1 << 20)
-        return 1;
-    return (int)std::min<size_t>(8, h / 64);
+    /* about one band per 8 MiB of float frame, at most 8 (measured on B200 + PCIe Gen5, scripts/e2e_probe.py: best
+     * counts 2-3 at 720p, 3-4 at 1080p, 4 at 1440p, 8 at 4K and 8K; each band costs ~10 API calls) */
+    const size_t bytes = (size_t)w * h * 12;
+    const size_t nb = (bytes + ((size_t)8 << 20) - 1) / ((size_t)8 << 20);
+    return (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, nb), h / 64));
 }
 
 int ensure_events(lumacu_ctx *ctx, int nb)

@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 import lumahdrv_b200 as L  # noqa: E402
 from lumahdrv_b200._lib import check  # noqa: E402
 
-W, H, N = 3840, 2160, 12
+W, H, N = (int(sys.argv[1]), int(sys.argv[2]), 12) if len(sys.argv) > 2 else (3840, 2160, 12)
 enc = L.LumaEncoder(0)
 enc.initialize(None, W, H)
 dec = L.LumaDecoder(0)
@@ -64,13 +64,16 @@ def t_both():
     return (time.perf_counter() - t0) / N * 1e3, res
 
 
-for nb in (1, 2, 8):
+for nb in (1, 2, 3, 4, 8):
     bands(nb)
     t_enc(); t_dec()
     e, d = t_enc(), t_dec()
     both, res = t_both()
     print(f"bands {nb:2d}: encode {e:6.3f} ms  decode {d:6.3f} ms  concurrent (independent loops) {both:6.3f} ms per frame pair "
           f"(enc {res['e']:.3f}, dec {res['d']:.3f})", flush=True)
+
+if len(sys.argv) > 2:
+    sys.exit(0)
 
 # ---- the bench's pipeline: encoder thread -> queue -> decoder thread, two plane slots
 import queue
