@@ -136,3 +136,22 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
         out = t.decode(ref_planes, w, h)
         assert torch.equal(out.view(torch.int32), ref_out.view(torch.int32)), f"decode variant {dec_v} cap {cap}"
     ctx.set_tuning(0, 0, 0)
+
+
+def test_plain_c_example_round_trips(torch_cuda):
+    """examples/roundtrip.c (strict C99 against include/lumacu.h) encodes and decodes a frame on the GPU."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "examples" / "roundtrip"
+    if not exe.exists():
+        gcc = shutil.which("gcc")
+        if not gcc:
+            pytest.skip("examples/roundtrip not built and no gcc")
+        subprocess.run([gcc, "-std=c99", "-O2", f"-I{root / 'include'}", str(root / "examples" / "roundtrip.c"),
+                        f"-L{root / 'lumahdrv_b200'}", "-llumacu", "-Wl,-rpath,$ORIGIN/../lumahdrv_b200", "-lm", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "worst relative round-trip error" in r.stdout

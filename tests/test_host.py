@@ -197,3 +197,28 @@ def test_thresholds_equal_reference_search_on_arbitrary_monotone_luts(lumalib, p
         bad = np.nonzero(got != want)[0]
         assert bad.size == 0, f"trial {trial} kind {kind}: val {probes[bad[0]]!r} -> {got[bad[0]]} vs reference {want[bad[0]]}"
     assert ran >= 40
+
+
+def test_c_abi_header_is_plain_c99_and_example_builds():
+    """include/lumacu.h must be consumable from C (no C++-isms): compile examples/roundtrip.c as strict C99, link it
+    against liblumacu.so, and -- without a GPU -- see it fail loudly at lumacu_create instead of computing on the CPU."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src, exe = root / "examples" / "roundtrip.c", root / "examples" / "roundtrip"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", f"-I{root / 'include'}", str(src)],
+                   check=True)
+    subprocess.run([gcc, "-std=c99", "-O2", f"-I{root / 'include'}", str(src), f"-L{root / 'lumahdrv_b200'}", "-llumacu",
+                    "-Wl,-rpath,$ORIGIN/../lumahdrv_b200", "-lm", "-o", str(exe)], check=True)
+    import torch
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "kernel launches" in r.stdout
+    else:
+        assert r.returncode == 1 and "LUMACU_ERR_NO_DEVICE" in r.stderr
