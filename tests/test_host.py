@@ -199,7 +199,7 @@ def test_thresholds_equal_reference_search_on_arbitrary_monotone_luts(lumalib, p
     assert ran >= 40
 
 
-def test_c_abi_header_is_plain_c99_and_example_builds():
+def test_c_abi_header_is_plain_c99_and_example_builds(lumalib):
     """include/lumacu.h must be consumable from C (no C++-isms): compile examples/roundtrip.c as strict C99, link it
     against liblumacu.so, and -- without a GPU -- see it fail loudly at lumacu_create instead of computing on the CPU."""
     import shutil
