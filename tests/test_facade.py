@@ -20,6 +20,10 @@ CS = {"LUV": 0, "RGB": 1, "YCBCR": 2, "XYZ": 3}
 
 
 def _build():
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import lumahdrv_b200
+    lumahdrv_b200.build_library()  # the facade links against liblumacu.so
     subprocess.run(["make", "-s", "-j", "8", "-C", str(CXX), f"REF={REF}"], check=True, capture_output=True)
 
 
