@@ -91,6 +91,7 @@ public:
     unsigned char **getBuffer() { return m_vpxFrame->planes; }
     LumaDecoderParams getParams() { return m_params; }
     void setParams(LumaDecoderParams params) { m_params = params; }
+    void setDevice(int device) { m_quant.setDevice(device); } /* addition: which GPU runs the transform */
 
 private:
     void registerPlanes();

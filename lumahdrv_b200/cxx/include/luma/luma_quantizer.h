@@ -56,6 +56,9 @@ public:
 
     /* ---- additions used by LumaEncoder / LumaDecoder of this facade ---- */
     lumacu_ctx *device() const;   /* context with the current quantizer uploaded; throws LumaException */
+    /* CUDA device this object computes on (default: environment variable LUMA_CUDA_DEVICE, else 0).  Must be called
+     * before the first use; one object per GPU (on its own host thread) is how a process drives several GPUs. */
+    void setDevice(int device);
     colorSpace_t colorSpace() const { return m_colorSpace; }
 
 private:
@@ -68,6 +71,7 @@ private:
     float m_Lmax, m_Lmin;
     unsigned int m_maxVal, m_maxValColor, m_bitdepth, m_bitdepthColor;
 
+    int m_device; /* -1 = take LUMA_CUDA_DEVICE */
     mutable lumacu_ctx *m_ctx;
     mutable std::vector<float> m_uploaded; /* what the device currently holds */
     mutable colorSpace_t m_uploadedCs;

@@ -35,7 +35,7 @@ void throw_status(lumacu_ctx *ctx, int rc, const char *what)
 
 LumaQuantizer::LumaQuantizer()
     : m_colorSpace(CS_LUV), m_Lmax(10000.0f), m_Lmin(0.005f), m_maxVal(0), m_maxValColor(0), m_bitdepth(0),
-      m_bitdepthColor(0), m_ctx(NULL), m_uploadedCs(CS_LUV), m_uploadedMaxValColor(0), m_uploadedLmax(0.0f)
+      m_bitdepthColor(0), m_device(-1), m_ctx(NULL), m_uploadedCs(CS_LUV), m_uploadedMaxValColor(0), m_uploadedLmax(0.0f)
 {
 }
 
@@ -92,7 +92,7 @@ void LumaQuantizer::sync() const
     if (m_mapping.empty())
         throw LumaException("LumaQuantizer: setQuantizer() has not been called");
     if (!m_ctx) {
-        const int rc = lumacu_create(env_device(), &m_ctx);
+        const int rc = lumacu_create(m_device >= 0 ? m_device : env_device(), &m_ctx);
         if (rc != LUMACU_OK) {
             m_ctx = NULL;
             throw_status(NULL, rc, "LumaQuantizer: no usable CUDA device (this build has no CPU path)");
@@ -111,6 +111,16 @@ void LumaQuantizer::sync() const
     m_uploadedCs = m_colorSpace;
     m_uploadedMaxValColor = m_maxValColor;
     m_uploadedLmax = m_Lmax;
+}
+
+void LumaQuantizer::setDevice(int device)
+{
+    if (m_ctx && lumacu_device(m_ctx) != device) { /* move: drop the old context, the next use re-uploads */
+        lumacu_destroy(m_ctx);
+        m_ctx = NULL;
+        m_uploaded.clear();
+    }
+    m_device = device;
 }
 
 lumacu_ctx *LumaQuantizer::device() const

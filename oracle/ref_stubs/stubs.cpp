@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <mutex>
 
 /* =========================== image allocation ============================== */
 /* Pitch rule of libvpx 1.6.1 vpx_img_alloc as the reference relies on it
@@ -233,13 +234,25 @@ static std::map<std::string, MkvStubFile> &registry()
     static std::map<std::string, MkvStubFile> r;
     return r;
 }
+/* the map itself is shared by every thread of a multi-GPU driver; each "file" is only touched by its owner, and
+ * std::map never moves its nodes, so only look-ups and insertions need the lock */
+static std::mutex &registry_mutex()
+{
+    static std::mutex m;
+    return m;
+}
 
 MkvStubFile *mkv_stub_find(const char *name)
 {
+    std::lock_guard<std::mutex> lock(registry_mutex());
     std::map<std::string, MkvStubFile>::iterator it = registry().find(name ? name : "");
     return it == registry().end() ? NULL : &it->second;
 }
-void mkv_stub_erase(const char *name) { registry().erase(name ? name : ""); }
+void mkv_stub_erase(const char *name)
+{
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    registry().erase(name ? name : "");
+}
 size_t mkv_stub_frame_count(const char *name)
 {
     MkvStubFile *f = mkv_stub_find(name);
@@ -263,6 +276,7 @@ MkvInterface::~MkvInterface() {}
 void MkvInterface::openWrite(const char *outputFile, const unsigned int, const unsigned int,
                              const float, const float)
 {
+    std::lock_guard<std::mutex> lock(registry_mutex());
     registry()[outputFile] = MkvStubFile();
     m_file = &registry()[outputFile];
 }

@@ -104,3 +104,24 @@ def test_reference_test_simple_enc_runs_on_facade():
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Encoding finished. 5 frames encoded." in r.stdout
     assert "Pixel transform:           CUDA" in r.stderr
+
+
+@pytest.mark.gpu
+def test_one_object_per_gpu_on_threads_is_independent_of_the_gpu_count():
+    """tests/cxx/multi_gpu.cpp: one LumaEncoder/LumaDecoder pair per GPU, each on its own host thread (setDevice), frame
+    f handled by GPU f mod N.  With one GPU visible this runs N = 1 and 'N = 2 objects on the same device' is covered by
+    running the driver twice; on a multi-GPU box the hashes per frame must not depend on N."""
+    import torch
+
+    if not (B / "multi_gpu").exists():
+        pytest.skip("tests/cxx/build/multi_gpu not built")
+    base = _run("multi_gpu", 1, 6, 640, 360)
+    assert base.returncode == 0, base.stdout + base.stderr
+    assert base.stdout.count("frame ") == 6
+    n = torch.cuda.device_count()
+    for gpus in sorted({min(2, n), n} - {1}):
+        other = _run("multi_gpu", gpus, 6, 640, 360)
+        assert other.returncode == 0, other.stdout + other.stderr
+        assert other.stdout == base.stdout, f"{gpus} GPUs"
+    # the same frames through the single-object round-trip driver's oracle build are covered by
+    # test_facade_equals_reference_through_public_api; here the reference is N = 1 itself
