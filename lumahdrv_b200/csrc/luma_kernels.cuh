@@ -234,6 +234,8 @@ template <int CS, bool SUB, int BYTES, bool VEC>
 __global__ void __launch_bounds__(kThreads) encode_kernel(const EncArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (CS == CS_YCBCR)
+        powf_tables_stage();
     const SearchCtx s = make_search_ctx(a.q, smem_raw);
     constexpr bool LUT_ALL = (CS == CS_RGB || CS == CS_XYZ); /* every plane goes through the LUT search */
     /* always the full key transform with its explicit NaN test: the shortcut `bits ^ 0x80000000` for
@@ -418,6 +420,8 @@ template <int CS, bool SUB, int BYTES, bool VEC>
 __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (CS == CS_YCBCR)
+        powf_tables_stage();
     constexpr bool LUT_ALL = (CS == CS_RGB || CS == CS_XYZ);
 
     const float *lut = a.q.lut;
@@ -581,6 +585,8 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const DecArgs a)
 template <int CS, bool FWD>
 __global__ void __launch_bounds__(kThreads) transform_kernel(float *c0, float *c1, float *c2, size_t n, float sc, float l_max)
 {
+    if (CS == CS_YCBCR)
+        powf_tables_stage();
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
         float a = c0[i], b = c1[i], c = c2[i];
         float x, y, z;

@@ -50,6 +50,22 @@ static __device__ const unsigned long long k_exp2f_tab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 
+/* Per-block shared-memory copies of the two tables: the lookups are data dependent (every lane its own entry), so
+ * constant memory would serialise them (measured: 2.5x slower) and global loads cost a 64-bit address, a descriptor
+ * and an L1 round trip each (~10 instructions of a ~75-instruction powf); LDS with a uniform base is one instruction.
+ * Every kernel that can reach powf_glibc stages them once with powf_tables_stage(). */
+static __shared__ double2 s_powf_log2_tab[16];
+static __shared__ unsigned long long s_exp2f_tab[32];
+
+__device__ __forceinline__ void powf_tables_stage() /* whole block; blockDim.x >= 32 */
+{
+    if (threadIdx.x < 16)
+        s_powf_log2_tab[threadIdx.x] = k_powf_log2_tab[threadIdx.x];
+    if (threadIdx.x < 32)
+        s_exp2f_tab[threadIdx.x] = k_exp2f_tab[threadIdx.x];
+    __syncthreads();
+}
+
 /* Polynomial coefficients live in constant memory so that DMUL / DADD take them as constant-bank operands; as
  * literals the compiler rebuilt each 64-bit value with two UMOVs at every use (15 % of the instruction stream).
  * [0..4] = __powf_log2_data.poly (A), [5..7] = __exp2f_data.poly_scaled (C). */
@@ -72,7 +88,7 @@ __device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
     const uint32_t top = tmp & 0xff800000u;
     const uint32_t iz = ix - top;
     const int k = (int32_t)top >> 23;
-    const double2 tc = k_powf_log2_tab[i];
+    const double2 tc = s_powf_log2_tab[i];
     const double z = (double)__uint_as_float(iz);
 
     const double A0 = k_powf_poly[0], A1 = k_powf_poly[1], A2 = k_powf_poly[2], A3 = k_powf_poly[3], A4 = k_powf_poly[4];
@@ -95,7 +111,7 @@ __device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
     const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
     kd = __dadd_rn(kd, -SHIFT);
     const double rr = __dadd_rn(ylogx, -kd);
-    unsigned long long t = k_exp2f_tab[ki & 31u];
+    unsigned long long t = s_exp2f_tab[ki & 31u];
     t += ki << (52 - 5);
     const double s = __longlong_as_double((long long)t);
     const double zz = __dadd_rn(__dmul_rn(C0, rr), C1);
