@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--enc", default="0,1004,3,5,84,34,44,54")
     ap.add_argument("--dec", default="0,3,5,14")
     ap.add_argument("--caps", default="0")
+    ap.add_argument("--preroll", type=float, default=0.0, help="seconds of the same work before timing (sustained, power-capped regime)")
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)
     a = ap.parse_args()
@@ -41,8 +42,14 @@ def main():
     res = []
 
     def timeit(fn):
-        for _ in range(5):
+        import time
+        t0 = time.perf_counter()
+        n = 0
+        while n < 5 or time.perf_counter() - t0 < a.preroll:
             fn()
+            n += 1
+            if n % 8 == 0:
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
         ev[0].record()
