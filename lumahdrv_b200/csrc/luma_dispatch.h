@@ -31,7 +31,7 @@ LUMA_DECL_GENERIC(3)
 constexpr int kEncVariantPlain = 4, kDecVariantPlain = 4;
 constexpr unsigned kEncStagedSmemBytes = 6u * 512u * 8u; /* luma_fast.cuh kEncStageBlock */
 #define LUMA_DECL_FAST(CSV)                                          \
-    enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk, int variant); \
+    enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk, int variant, bool prescale); \
     dec_fn get_decode_fast_cs##CSV(bool sub, int bytes, int variant);
 LUMA_DECL_FAST(0)
 LUMA_DECL_FAST(1)

@@ -847,13 +847,13 @@ dec_fn pick_dec(int cs, bool sub, int bytes, bool vec)
     default: return get_decode_generic_cs3(sub, bytes, vec);
     }
 }
-enc_fn pick_enc_fast(int cs, bool sub, int bytes, int walk, int variant)
+enc_fn pick_enc_fast(int cs, bool sub, int bytes, int walk, int variant, bool prescale)
 {
     switch (cs) {
-    case CS_LUV: return get_encode_fast_cs0(sub, bytes, walk, variant);
-    case CS_RGB: return get_encode_fast_cs1(sub, bytes, walk, variant);
-    case CS_YCBCR: return get_encode_fast_cs2(sub, bytes, walk, variant);
-    default: return get_encode_fast_cs3(sub, bytes, walk, variant);
+    case CS_LUV: return get_encode_fast_cs0(sub, bytes, walk, variant, prescale);
+    case CS_RGB: return get_encode_fast_cs1(sub, bytes, walk, variant, prescale);
+    case CS_YCBCR: return get_encode_fast_cs2(sub, bytes, walk, variant, prescale);
+    default: return get_encode_fast_cs3(sub, bytes, walk, variant, prescale);
     }
 }
 dec_fn pick_dec_fast(int cs, bool sub, int bytes, int variant)
@@ -1032,15 +1032,15 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
         const bool direct = ctx->q.dtab && !ctx->no_direct;
         const int walk_direct = ctx->q.d_lo_key ? -1 : 0; /* -1: direct table that needs the lower clamp too */
         int walk = direct ? walk_direct : (int)ctx->q.walk;
-        fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
+        fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         if (!fn && direct) { /* tuning variants exist for one search flavour only */
             walk = (int)ctx->q.walk;
-            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
+            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (!fn && variant != kEncVariantPlain) {
             variant = kEncVariantPlain;
             walk = direct ? walk_direct : (int)ctx->q.walk;
-            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant);
+            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (fn && walk <= 0)
             smem = (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
