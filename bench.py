@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames per worker in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the second, power-capped-regime measurement")
     return ap.parse_args()
 
 
@@ -117,20 +118,31 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def finish(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        self.proc = None
+        self.done = True
+
+    def window(self, t_begin: float, t_end: float) -> dict:
+        """Clocks / power / throttle reasons of the samples received inside [t_begin, t_end] (nvidia-smi reports with
+        about one sampling period of delay, hence the small margin)."""
+        if not getattr(self, "done", False) and not self.lines:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        lines = [ln for t, ln in self.lines if t_begin <= t <= t_end + 0.05]
+        if not lines:
+            lines = [ln for _, ln in self.lines[-3:]]
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -255,46 +267,64 @@ def ours_arm(args):
         if world > 1:
             dist.barrier()
 
-    # warm-up: at least W (>= 3) steps, and at least ~0.4 s of work so that the memory clocks have left their idle
-    # state (measured: the first ~100 ms after an idle period run the same kernels ~5 % slower)
-    n_warm = 0
-    t_w0 = time.perf_counter()
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w0 < 0.4:
-        step()
-        n_warm += 1
-        if n_warm % 8 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-
-    # ---- timed region: K steps, CUDA events on the launching stream, per-kernel events inside
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    launches0 = t.launch_count
-    barrier()
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
+        step()
     torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        ev[k][0].record()
-        t.encode(rgb, planes=planes, stats=stats)
-        ev[k][1].record()
-        t.decode(planes, W, H, out=out)
-        ev[k][2].record()
-    torch.cuda.synchronize()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = t.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    tt = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms = (float(v) for v in tt.tolist())
+    def timed(n_steps):
+        """n_steps steps bracketed by barrier + synchronize; CUDA events on the launching stream around every kernel."""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(n_steps):
+            ev[k][0].record()
+            t.encode(rgb, planes=planes, stats=stats)
+            ev[k][1].record()
+            t.decode(planes, W, H, out=out)
+            ev[k][2].record()
+        torch.cuda.synchronize()
+        barrier()
+        t1 = time.perf_counter()
+        tot = ev[0][0].elapsed_time(ev[-1][2])
+        enc = sum(e[0].elapsed_time(e[1]) for e in ev) / n_steps
+        dec = sum(e[1].elapsed_time(e[2]) for e in ev) / n_steps
+        tt = torch.tensor([tot, enc, dec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tt.tolist()] + [t0, t1]
+
+    # ---- timed region: W warm-up steps (above), then exactly K steps
+    launches0 = t.launch_count
+    total_ms, enc_ms, dec_ms, t_wall0, t_wall1 = timed(args.steps)
+    t_wall = t_wall1 - t_wall0
+    launches = t.launch_count - launches0
+
+    # ---- the same measurement in the sustained regime: ~0.5 s of back-to-back steps first, so that the board sits at
+    # its power cap (SM clock ~1.7-1.9 GHz) when the clock starts.  Reported next to `value`, not instead of it.
+    sustained = None
+    if not args.no_sustained:
+        t_p0 = time.perf_counter()
+        n_pre = 0
+        while time.perf_counter() - t_p0 < 0.5:
+            step()
+            n_pre += 1
+            if n_pre % 8 == 0:
+                torch.cuda.synchronize()
+        s_tot, s_enc, s_dec, s_t0, s_t1 = timed(args.steps)
+        sustained = {"value": world * F * W * H * args.steps / (s_tot / 1e3) / 1e6, "unit": "Mpixels/s", "preroll_steps": n_pre,
+                     "encode_ms": s_enc, "decode_ms": s_dec, "window": (s_t0, s_t1)}
+    if rank == 0:
+        sampler.finish()
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
+    if sustained is not None:
+        w0, w1 = sustained.pop("window")
+        sustained["clocks"] = sampler.window(w0, w1) if rank == 0 else None
+
     px_step = F * W * H  # per GPU
     value = world * px_step * args.steps / (total_ms / 1e3) / 1e6
 
@@ -455,6 +485,7 @@ def ours_arm(args):
                          "copy_gbs_this_lease": copy_gbs},
             "gpu_launches": launches,
             "clocks": clocks,
+            "sustained": sustained,
             "host_cpus_bound": affinity,
             "wall_s_timed_region": t_wall,
         }
