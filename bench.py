@@ -134,10 +134,10 @@ class ClockSampler:
 
     def window(self, t_begin: float, t_end: float) -> dict:
         """Clocks / power / throttle reasons of the samples received inside [t_begin, t_end] (nvidia-smi reports with
-        about one sampling period of delay, hence the small margin)."""
+        about one sampling period (20 ms) of delay, hence the shifted window)."""
         if not getattr(self, "done", False) and not self.lines:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        lines = [ln for t, ln in self.lines if t_begin <= t <= t_end + 0.05]
+        lines = [ln for t, ln in self.lines if t_begin + 0.02 <= t <= t_end + 0.02]
         if not lines:
             lines = [ln for _, ln in self.lines[-3:]]
         sm, mx, power, reasons = [], [], [], set()
