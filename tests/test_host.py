@@ -222,3 +222,20 @@ def test_c_abi_header_is_plain_c99_and_example_builds(lumalib):
         assert "kernel launches" in r.stdout
     else:
         assert r.returncode == 1 and "LUMACU_ERR_NO_DEVICE" in r.stderr
+
+
+def test_bench_cuda_arm_refuses_to_run_without_a_gpu():
+    """No silent CPU fallback: without a CUDA device the CUDA arm of bench.py stops with a clear message."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout)
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
