@@ -23,6 +23,7 @@
 #include <cuda.h> /* CUtensorMap + enums only; the encoder entry point is resolved at run time */
 
 #include <algorithm>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -142,12 +143,27 @@ int fail(lumacu_ctx *ctx, int code, const char *fmt, ...)
                         "%s failed: %s", #expr, cudaGetErrorString(e_));                         \
     } while (0)
 
+/* No exception crosses the C ABI (lumacu.h): every entry point is a function-try-block ending in this. */
+int on_exception(lumacu_ctx *ctx, bool oom) noexcept
+{
+    try {
+        return fail(ctx, oom ? LUMACU_ERR_OUT_OF_MEMORY : LUMACU_ERR_CUDA,
+                    oom ? "host allocation failed (std::bad_alloc)" : "unexpected C++ exception");
+    } catch (...) {
+        return oom ? LUMACU_ERR_OUT_OF_MEMORY : LUMACU_ERR_CUDA;
+    }
+}
+#define LUMACU_CATCH(ctx_expr)                                  \
+    catch (const std::bad_alloc &) { return on_exception(ctx_expr, true); } \
+    catch (...) { return on_exception(ctx_expr, false); }
+
 int reserve(lumacu_ctx *ctx, DeviceBuffer &b, size_t bytes)
 {
     if (bytes <= b.cap)
         return LUMACU_OK;
     if (b.p) {
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        /* launches on caller-provided streams may still use the old buffer */
+        CU_TRY(ctx, cudaDeviceSynchronize());
         cudaFree(b.p);
         b.p = nullptr;
         b.cap = 0;
@@ -211,7 +227,7 @@ extern "C" const char *lumacu_status_name(int status)
 }
 
 extern "C" int lumacu_device_count(int *count)
-{
+try {
     if (!count)
         return LUMACU_ERR_INVALID_ARGUMENT;
     int n = 0;
@@ -224,6 +240,7 @@ extern "C" int lumacu_device_count(int *count)
     *count = n;
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_have_ptf_tables(void)
 {
@@ -255,7 +272,7 @@ static float host_pq_encode(float val, float L)
 }
 
 extern "C" int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float min_lum, float *lut_out, size_t cap)
-{
+try {
     if (!lut_out || bitdepth > 16)
         return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_build_lut: bad arguments");
     const unsigned max_val = (unsigned)((int)powf(2.0f, (float)bitdepth) - 1);
@@ -305,6 +322,7 @@ extern "C" int lumacu_build_lut(int ptf, unsigned bitdepth, float max_lum, float
     return LUMACU_OK;
 #endif
 }
+LUMACU_CATCH(nullptr)
 
 /* Thresholds of the reference's nearest-code decision.  Returns 1 and fills
  * thr_keys[0 .. lut_len-2] (ordered keys, strictly increasing) when the LUT is
@@ -377,7 +395,7 @@ void put_record(uint8_t *&p, uint32_t id, const void *payload, uint32_t size)
 
 extern "C" int lumacu_metadata_pack(const lumacu_metadata *m, const float *lut, uint32_t lut_len, uint8_t *blob, size_t cap,
                                     size_t *used)
-{
+try {
     if (!m || !lut || lut_len < 1 || !used)
         return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_pack: NULL argument");
     const uint32_t table_bytes = (lut_len - 1) * 4u; /* getSize() = maxVal floats, one short of the table */
@@ -396,10 +414,11 @@ extern "C" int lumacu_metadata_pack(const lumacu_metadata *m, const float *lut, 
     put_record(p, 436, range, 8);
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_metadata_unpack(const uint8_t *blob, size_t size, lumacu_metadata *m, float *lut_out, size_t lut_cap,
                                       uint32_t *lut_len)
-{
+try {
     if (!blob || !m || !lut_out || !lut_len)
         return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_metadata_unpack: NULL argument");
     /* defaults of LumaDecoderParams (include/luma/luma_decoder.h:60-70,112-120) for the optional records */
@@ -444,11 +463,12 @@ extern "C" int lumacu_metadata_unpack(const uint8_t *blob, size_t size, lumacu_m
     *lut_len = (uint32_t)n_lut;
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 /* ================================ context ============================================ */
 
 extern "C" int lumacu_create(int device, lumacu_ctx **out)
-{
+try {
     if (!out)
         return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_create: out is NULL");
     *out = nullptr;
@@ -486,6 +506,7 @@ extern "C" int lumacu_create(int device, lumacu_ctx **out)
     *out = ctx;
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_destroy(lumacu_ctx *ctx)
 {
@@ -517,18 +538,19 @@ extern "C" int lumacu_device(const lumacu_ctx *ctx) { return ctx ? ctx->device :
 extern "C" uint64_t lumacu_launch_count(const lumacu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int lumacu_synchronize(lumacu_ctx *ctx)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" void *lumacu_stream(lumacu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int lumacu_host_register(void *p, size_t bytes)
-{
+try {
     if (!p || !bytes)
         return LUMACU_ERR_INVALID_ARGUMENT;
     cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
@@ -542,18 +564,20 @@ extern "C" int lumacu_host_register(void *p, size_t bytes)
     }
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_host_unregister(void *p)
-{
+try {
     if (!p)
         return LUMACU_OK;
     if (cudaHostUnregister(p) != cudaSuccess)
         cudaGetLastError();
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_host_alloc(size_t bytes, void **out)
-{
+try {
     if (!out)
         return LUMACU_ERR_INVALID_ARGUMENT;
     cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
@@ -564,25 +588,30 @@ extern "C" int lumacu_host_alloc(size_t bytes, void **out)
     }
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 extern "C" int lumacu_host_free(void *p)
-{
+try {
     if (p)
         cudaFreeHost(p);
     return LUMACU_OK;
 }
+LUMACU_CATCH(nullptr)
 
 /* ================================ quantizer ========================================== */
 
 extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t lut_len, uint32_t max_val_color,
                                     int color_space, float max_lum)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!lut || lut_len < 1 || lut_len > 65536u)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: lut_len %u not in [1,65536]", lut_len);
     if (color_space < 0 || color_space > 3)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: unknown colour space %d", color_space);
+    /* 2^colorBitDepth - 1 with a colour depth the 16-bit container can hold (attachment 431 is untrusted input) */
+    if (max_val_color < 1 || max_val_color > 65535u)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: max_val_color %u not in [1,65535]", max_val_color);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
 
     const uint32_t max_val = lut_len - 1;
@@ -708,8 +737,8 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
     int rc = reserve(ctx, ctx->d_tables, total);
     if (rc)
         return rc;
-    /* previous launches may still read the old tables */
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    /* previous launches (on the context's stream or on a caller's) may still read the old tables */
+    CU_TRY(ctx, cudaDeviceSynchronize());
     unsigned char *d = (unsigned char *)ctx->d_tables.p;
     CU_TRY(ctx, cudaMemcpy(d, lut, (size_t)lut_len * 4, cudaMemcpyHostToDevice));
     if (thr_count)
@@ -774,9 +803,10 @@ extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t 
     ctx->configured = true;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift, uint32_t *walk)
-{
+try {
     if (!ctx || !ctx->configured)
         return LUMACU_ERR_NOT_CONFIGURED;
     if (mode)
@@ -789,9 +819,10 @@ extern "C" int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_
         *walk = ctx->q.walk;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_set_kernel_path(lumacu_ctx *ctx, int path)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (path != 0 && path != 1)
@@ -799,11 +830,12 @@ extern "C" int lumacu_set_kernel_path(lumacu_ctx *ctx, int path)
     ctx->force_generic = (path == 1);
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_last_kernel_path(const lumacu_ctx *ctx) { return (ctx && ctx->last_fast) ? 1 : 0; }
 
 extern "C" int lumacu_set_host_bands(lumacu_ctx *ctx, int bands)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (bands < 0 || bands > 64)
@@ -811,9 +843,10 @@ extern "C" int lumacu_set_host_bands(lumacu_ctx *ctx, int bands)
     ctx->host_bands = bands;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (enc_variant < 0 || dec_variant < 0 || blocks_per_sm_cap < 0)
@@ -825,6 +858,7 @@ extern "C" int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_varia
     ctx->grid_tpt = blocks_per_sm_cap / 100;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 /* ================================ launches ============================================ */
 namespace {
@@ -1079,10 +1113,11 @@ extern "C" int lumacu_encode_dev(lumacu_ctx *ctx, const float *d_rgb, float *d_r
                                  int profile, float pre_scaling, uint8_t *const d_planes[3], const int32_t strides[3],
                                  uint32_t n_frames, size_t rgb_frame_stride, const size_t plane_frame_stride[3],
                                  lumacu_frame_stats *d_stats, void *stream)
-{
+try {
     return encode_launch(ctx, d_rgb, d_rgb_out, w, h, profile, pre_scaling, d_planes, strides, n_frames, rgb_frame_stride,
                          plane_frame_stride, d_stats, stream, LaunchOpts());
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
                          int profile, float pre_scaling, float *d_rgb, uint32_t n_frames, size_t rgb_frame_stride,
@@ -1150,7 +1185,8 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
         }
         vec = vec && aligned(a.rgba, 16) && (a.rgba_frame_stride % 16 == 0);
     }
-    if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !opt.passthrough && !opt.display) {
+    /* the tuned kernel walks whole 2-row tiles: odd heights (legal for 4:4:4 decode) take the generic kernel */
+    if (vec && (h % 2 == 0) && small32 && ctx->smem_dec_fast && !ctx->force_generic && !opt.passthrough && !opt.display) {
         fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
         if (!fn)
             fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
@@ -1173,17 +1209,18 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
 extern "C" int lumacu_decode_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
                                  uint32_t h, int profile, float pre_scaling, float *d_rgb, uint32_t n_frames,
                                  size_t rgb_frame_stride, const size_t plane_frame_stride[3], void *stream)
-{
+try {
     return decode_launch(ctx, d_planes, strides, w, h, profile, pre_scaling, d_rgb, n_frames, rgb_frame_stride, plane_frame_stride,
                          stream, LaunchOpts());
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 /* ---- display decode ------------------------------------------------------------------- */
 extern "C" int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes[3], const int32_t strides[3], uint32_t w,
                                   uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
                                   uint8_t *d_rgba, int32_t rgba_pitch, uint32_t n_frames, const size_t plane_frame_stride[3],
                                   size_t rgba_frame_stride, void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!params || !d_rgba)
@@ -1201,10 +1238,11 @@ extern "C" int lumacu_display_dev(lumacu_ctx *ctx, const uint8_t *const d_planes
     opt.rgba_frame_stride = rgba_frame_stride ? rgba_frame_stride : (size_t)rgba_pitch * h;
     return decode_launch(ctx, d_planes, strides, w, h, profile, pre_scaling, nullptr, n_frames, 0, plane_frame_stride, stream, opt);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 /* ---- frame sources on the device ------------------------------------------------------------------------ */
 extern "C" int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, uint32_t h, void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!d_rgb || !w || !h)
@@ -1218,10 +1256,11 @@ extern "C" int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, 
     ctx->launches++;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba_half, uint32_t w, uint32_t h, int channels,
                                              float *d_rgb, void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!d_rgba_half || !d_rgb || !w || !h)
@@ -1240,10 +1279,11 @@ extern "C" int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba
     ctx->launches++;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame, uint32_t w, uint32_t h, int to_cs, float sc,
                                                 void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
@@ -1263,6 +1303,7 @@ extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame,
     ctx->launches++;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 static bool channel_uses_lut(const lumacu_ctx *ctx, unsigned ch)
 {
@@ -1270,7 +1311,7 @@ static bool channel_uses_lut(const lumacu_ctx *ctx, unsigned ch)
 }
 
 extern "C" int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch, void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
@@ -1290,9 +1331,10 @@ extern "C" int lumacu_quantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_
     ctx->launches++;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *d_out, size_t n, unsigned ch, void *stream)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
@@ -1309,6 +1351,7 @@ extern "C" int lumacu_dequantize_dev(lumacu_ctx *ctx, const float *d_in, float *
     ctx->launches++;
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 /* ================================ host-pointer entry points ========================== */
 namespace {
@@ -1456,9 +1499,10 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
 extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
                              uint8_t *const planes[3], const int32_t strides[3], int write_back,
                              lumacu_frame_stats *stats)
-{
+try {
     return host_encode(ctx, rgb, w, h, profile, pre_scaling, planes, strides, write_back, stats, false);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
                        int profile, float pre_scaling, float *rgb, bool passthrough)
@@ -1520,14 +1564,15 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
 
 extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
                              uint32_t h, int profile, float pre_scaling, float *rgb)
-{
+try {
     return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, rgb, false);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
                               int profile, float pre_scaling, const lumacu_display_params *params, uint8_t *rgba,
                               int32_t rgba_pitch)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
@@ -1564,25 +1609,28 @@ extern "C" int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], c
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_quantize_planes(lumacu_ctx *ctx, const float *frame, uint32_t w, uint32_t h, int profile,
                                       uint8_t *const planes[3], const int32_t strides[3], lumacu_frame_stats *stats)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     return host_encode(ctx, const_cast<float *>(frame), w, h, profile, 1.0f, planes, strides, 0, stats, true);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_dequantize_planes(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
                                         uint32_t w, uint32_t h, int profile, float *frame)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     return host_decode(ctx, planes, strides, w, h, profile, 1.0f, frame, true);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint32_t w, uint32_t h, int to_cs, float sc)
-{
+try {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
@@ -1604,6 +1652,7 @@ extern "C" int lumacu_transform_color_space(lumacu_ctx *ctx, float *frame, uint3
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LUMACU_OK;
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 static int elementwise_host(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch, bool quant)
 {
@@ -1631,11 +1680,13 @@ static int elementwise_host(lumacu_ctx *ctx, const float *in, float *out, size_t
 }
 
 extern "C" int lumacu_quantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch)
-{
+try {
     return elementwise_host(ctx, in, out, n, ch, true);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 extern "C" int lumacu_dequantize(lumacu_ctx *ctx, const float *in, float *out, size_t n, unsigned ch)
-{
+try {
     return elementwise_host(ctx, in, out, n, ch, false);
 }
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))

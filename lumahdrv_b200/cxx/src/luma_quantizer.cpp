@@ -71,6 +71,10 @@ std::string LumaQuantizer::name(colorSpace_t cs)
 void LumaQuantizer::setQuantizer(ptf_t ptf, unsigned int bitdepth, colorSpace_t cs, unsigned int bitdepthC,
                                  float maxLum, float minLum)
 {
+    /* depths come straight from attachments 430/431 in the decoder (src/luma_decoder.cpp:79-100): refuse what the
+     * 16-bit container cannot hold before sizing the table from them */
+    if (bitdepth < 1 || bitdepth > 16 || bitdepthC < 1 || bitdepthC > 16)
+        throw LumaException("LumaQuantizer::setQuantizer: bit depths must be in [1,16]");
     m_colorSpace = cs;
     m_bitdepth = bitdepth;
     m_bitdepthColor = bitdepthC;

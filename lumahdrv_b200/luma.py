@@ -297,7 +297,27 @@ class LumaEncoder:
         return True
 
     def setChannels(self, frame: np.ndarray, planes=None):
-        return self.encode(frame, planes)
+        """LumaEncoder::setChannels (src/luma_encoder.cpp:196-201): `frame` is ALREADY colour-transformed
+        (LumaQuantizer.transformColorSpace(frame, True, sc)); [2x2 mean,] quantize and pack only."""
+        if not self.m_initialized:
+            raise LumaException("LumaEncoder: not initialized", 3)
+        _check_frame(frame)
+        _, h, w = frame.shape
+        if (w, h) != (self.width, self.height):
+            raise LumaException("Invalid frame size")
+        planes = planes if planes is not None else self.m_rawFrame
+        q = self.m_quant
+        q._upload()
+        ptrs, strides = _plane_args(planes)
+        st = FrameStats()
+        hnd = q.ctx.handle
+        check(q._lib.lumacu_quantize_planes(hnd, frame.ctypes.data, w, h, self.m_params.profile, ptrs, strides, C.byref(st)),
+              hnd, "lumacu_quantize_planes")
+        mean = st.sum / (w * h)
+        self.last_stats = {"sum": st.sum, "mean": mean, "max": st.max, "min": st.min}
+        if mean <= 1.0:  # src/luma_encoder.cpp:314-316
+            self.warnings.append("Warning! Mean luminance is %f cd/m2. Is the input calibrated to physical units?" % mean)
+        return planes
 
     def encode(self, frame: np.ndarray, planes=None):
         """LumaEncoder::encode (include/luma/luma_encoder.h:142-148) minus run():
@@ -394,6 +414,22 @@ class LumaDecoder:
         hnd = q.ctx.handle
         check(q._lib.lumacu_decode(hnd, ptrs, strides, w, h, profile, float(self.m_params.preScaling),
                                    self.m_frame.ctypes.data), hnd, "lumacu_decode")
+        return self.m_frame
+
+    def getVpxChannels(self, planes, w: int, h: int, profile: int | None = None) -> np.ndarray:
+        """LumaDecoder::getVpxChannels (src/luma_decoder.cpp:205-240): unpack, dequantize, [2x2 replicate]; the
+        result still has to go through LumaQuantizer.transformColorSpace(frame, False, sc)."""
+        if not self.m_initialized:
+            raise LumaException("LumaDecoder: not initialized", 3)
+        profile = self.m_params.profile if profile is None else int(profile)
+        if self.m_frame is None or self.m_frame.shape != (3, h, w):
+            self.m_frame = np.empty((3, h, w), dtype=np.float32)
+        q = self.m_quant
+        q._upload()
+        ptrs, strides = _plane_args(planes)
+        hnd = q.ctx.handle
+        check(q._lib.lumacu_dequantize_planes(hnd, ptrs, strides, w, h, profile, self.m_frame.ctypes.data), hnd,
+              "lumacu_dequantize_planes")
         return self.m_frame
 
     def display(self, planes, w: int, h: int, exposure: float = 1.0, gamma: float = 2.2, user_scaling: float = 1.0,

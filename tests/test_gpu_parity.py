@@ -385,6 +385,88 @@ def test_ycbcr_powf_dense(L, po):
         assert bits_equal(inv_gpu, inv_cpu), f"inverse, max ulp {max_ulp(inv_gpu, inv_cpu)}"
 
 
+@pytest.mark.parametrize("profile", [1, 3])
+@pytest.mark.parametrize("w,h", [(64, 33), (128, 1), (36, 7)])
+def test_odd_height_444_decode(L, po, w, h, profile):
+    """4:4:4 decode accepts odd heights (plane dims are rounded up, src/luma_decoder.cpp:211-214); the tuned kernel
+    walks 2-row tiles, so these sizes must take the generic kernel and still write the last row."""
+    nbytes = 2 if profile > 1 else 1
+    bits = 11 if profile > 1 else 8
+    _, o = make_pair(L, po, bits=bits, profile=profile)
+    rng = np.random.default_rng(w * 7 + h)
+    planes = L.alloc_planes(w, h, profile)
+    for p, (pl, (pw, ph)) in enumerate(zip(planes, L.plane_dims(w, h, profile))):
+        codes = rng.integers(0, (1 << bits) if p == 0 else 256, size=(ph, pw), dtype=np.uint32)
+        if nbytes == 2:
+            pl[:, : pw * 2] = codes.astype("<u2").view(np.uint8).reshape(ph, pw * 2)
+        else:
+            pl[:, :pw] = codes.astype(np.uint8)
+    dec = L.LumaDecoder()
+    dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=L.CS_LUV, ptfBitDepth=bits, colorBitDepth=8, profile=profile))
+    dec.initialize()
+    want = o.decode(planes, w, h, profile, 1.0)
+    for path in (0, 1):
+        dec.m_quant.ctx.set_kernel_path(path)
+        dec.m_frame = np.full((3, h, w), np.float32(-7.0))
+        got = dec.decode(planes, w, h)
+        assert bits_equal(got, want), f"kernel path {path}"
+        if h % 2:
+            assert dec.m_quant.ctx.last_kernel_path == 0  # generic
+    # device entry point, batch of 2 frames
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+    t = DeviceTransform(0, ptf="PQ", ptfBitDepth=bits, colorBitDepth=8, profile=profile)
+    dpl = [torch.from_numpy(np.stack([pl, pl])).cuda() for pl in planes]
+    out = t.decode(dpl, w, h, out=torch.full((2, 3, h, w), -7.0, device="cuda"))
+    torch.cuda.synchronize()
+    for f in range(2):
+        assert bits_equal(out[f].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("cs", CS)
+@pytest.mark.parametrize("profile", [0, 3])
+def test_unfused_halves_equal_fused(L, po, cs, profile):
+    """The reference's unfused sequences: transformColorSpace(frame, true, sc) + setChannels(frame)
+    (src/luma_encoder.cpp:196-201) and getVpxChannels + transformColorSpace(frame, false, sc)
+    (include/luma/luma_decoder.h:150-156) give the same bits as encode() / decode()."""
+    sc = 2.5
+    bits = 8 if profile < 2 else 11
+    enc, o = make_pair(L, po, bits=bits, cs=cs, profile=profile, sc=sc)
+    w, h = 96, 40
+    frame = adversarial_frame(w, h, lut=o.getMapping(), seed=9)
+    enc.initialize(None, w, h)
+    fused = [p.copy() for p in enc.encode(frame.copy(), L.alloc_planes(w, h, profile))]
+    f2 = frame.copy()
+    assert enc.m_quant.transformColorSpace(f2, True, sc)
+    unfused = enc.setChannels(f2, L.alloc_planes(w, h, profile))
+    ref_planes, _ = o.encode(frame.copy(), profile, sc)
+    nb = 2 if profile > 1 else 1
+    for a, b, c, (pw, ph) in zip(fused, unfused, ref_planes, po.plane_dims(w, h, profile)):
+        assert np.array_equal(a[:ph, :pw * nb], c[:ph, :pw * nb])
+        assert np.array_equal(b[:ph, :pw * nb], c[:ph, :pw * nb])
+    dec = L.LumaDecoder()
+    pr = enc.getParams()
+    dec.setParams(L.LumaDecoderParams(ptf=pr.ptf, colorSpace=pr.colorSpace, preScaling=sc, ptfBitDepth=bits, colorBitDepth=8,
+                                      profile=profile))
+    dec.initialize()
+    want = o.decode(ref_planes, w, h, profile, sc)
+    half = dec.getVpxChannels(ref_planes, w, h).copy()
+    assert dec.m_quant.transformColorSpace(half, False, sc)
+    assert max_ulp(half, want) <= FLOAT_ULP_TOL[cs]
+    assert max_ulp(dec.decode(ref_planes, w, h), want) <= FLOAT_ULP_TOL[cs]
+
+
+def test_set_quantizer_rejects_untrusted_sizes(L):
+    """attachment 431 (colour bit depth) is untrusted input: no multi-GB table, no exception across the C ABI"""
+    q = L.LumaQuantizer()
+    lib, h = L.lib(), q.ctx.handle
+    lut = L.build_lut("PQ", 11)
+    for bad in (0, 65536, 2**31 - 1):
+        assert lib.lumacu_set_quantizer(h, lut.ctypes.data, lut.size, bad, 0, 1e4) == 1
+        assert b"max_val_color" in lib.lumacu_last_error(h)
+    assert lib.lumacu_set_quantizer(h, lut.ctypes.data, lut.size, 65535, 0, 1e4) == 0
+
+
 def test_zz_both_kernel_families_were_exercised(L):
     """Runs last in this module: the parity cases above must have hit the tuned AND the generic kernels."""
     if not KERNEL_PATHS_SEEN:
