@@ -13,6 +13,11 @@ VP9) for every frame, then LumaDecoder::decode for every frame.
              host buffers; H2D/D2H copies inside the timed region
 * roofline   algorithmic bytes (15 B/px per direction) / measured kernel time vs the measured HBM peak
 * cpu_baseline  the reference's own CPU code (oracle/_ref) on this box's host cores, bounded sample
+* parity     outside the timed region every rank copies one WHOLE frame of the benchmark's own input, its planes and
+             its decoded floats to the host and has the CPU checker (oracle/parity_check.py, own process) redo it:
+             mismatching plane bytes (summed over ranks) and max ulp of the decoded floats (max over ranks)
+* configs    the other BASELINE.json configurations (cfg2 1080p, cfg3 4K PQ-10 YCbCr, cfg4 4K LOG-12, cfg5 8K + per-frame
+             sum/max of Y), same timing code, a few steps each, each with its own whole-frame parity check
 
 --impl reference times the reference CPU implementation instead (rank 0 only).
 """
@@ -35,6 +40,27 @@ BYTES_PER_PX_PASS = 15.0  # 12 B f32 RGB + 2 B Y + 2 * 2 B / 4 chroma (SURVEY 8d
 WORKLOAD = "4K (3840x2160) f32 RGB, PQ, Lu'v' 11/8-bit, profile 2 (4:2:0 LE16): encode+decode round trip"
 
 
+# The other BASELINE.json configurations; all profile 2 = 15 B/px per direction.
+OTHER_CONFIGS = {
+    "cfg2": dict(label="1920x1080 PQ Lu'v' 11/8-bit, profile 2", w=1920, h=1080, ptf="PQ", bits=11, cs="LUV", cbits=8,
+                 frames=64, stats=False),
+    "cfg3": dict(label="3840x2160 PQ 10-bit + BT.2020 YCbCr 10-bit (HDR10-equivalent), profile 2", w=3840, h=2160, ptf="PQ",
+                 bits=10, cs="YCBCR", cbits=10, frames=8, stats=False),
+    "cfg4": dict(label="3840x2160 LOG 12-bit + Lu'v' 8-bit, profile 2, frame stream sharded over the ranks", w=3840, h=2160,
+                 ptf="LOG", bits=12, cs="LUV", cbits=8, frames=32, min_total_frames=64, stats=False),
+    "cfg5": dict(label="7680x4320 PQ Lu'v' 11/8-bit, 0.005..10000 cd/m2, per-frame sum/max/min of Y", w=7680, h=4320, ptf="PQ",
+                 bits=11, cs="LUV", cbits=8, frames=8, stats=True),
+}
+
+
+def config_dict(n_gpus: int, frames: int) -> dict:
+    """`config` of the JSON line: the same object in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames,
+            "input": "seeded log-uniform noise 0.005..1e4 cd/m2, distinct per frame",
+            "l2": f"inputs larger than L2: {frames * (12 + 3 + 12) * W * H / 1e6:.0f} MB touched per step per GPU vs 126 MB L2",
+            "parallelism": f"frame shards x{n_gpus}, LUT broadcast only"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -47,6 +73,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the second, power-capped-regime measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity checks against the CPU checker")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg2..cfg5 block")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed steps per configuration of the configs block")
     return ap.parse_args()
 
 
@@ -70,6 +99,19 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the workers are forked pool processes that exit without the driver's loader hook seeing them: open the very
+    # library they time in this process too, once (dlopen only, nothing is computed here)
+    ref_so = None
+    try:
+        from oracle import pyoracle as po
+        if po.reference_available():
+            po._ref_lib()
+            ref_so = str(po.REF_SO.relative_to(ROOT))
+        else:
+            po._oracle_lib()
+            ref_so = str(po.ORACLE_SO.relative_to(ROOT))
+    except Exception as e:  # noqa: BLE001
+        ref_so = f"unavailable in parent: {e}"
     res = None
     times = []
     for i in range(args.warmup + args.steps):
@@ -85,11 +127,11 @@ def reference_arm(args):
         "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": px_per_step / value / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": res["cores"] * args.cpu_frames,
-                   "note": "reference CPU implementation (LumaEncoder::encode + LumaDecoder::decode, VP9 stubbed out), "
-                           "one independent frame stream per host core"},
+        "config": config_dict(args.gpus, args.frames),
+        "note": "reference CPU implementation (LumaEncoder::encode + LumaDecoder::decode, VP9 stubbed out), one independent "
+                f"frame stream per host core; each step = {res['cores'] * args.cpu_frames} frames of the workload",
         "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": res["cores"], "kind": res["kind"],
-                         "sample": res["sample"], "per_core_mpx_s": res["per_core_mpx_s"]},
+                         "sample": res["sample"], "per_core_mpx_s": res["per_core_mpx_s"], "library": ref_so},
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,15 +242,158 @@ def bind_to_gpu_numa(index: int):
     return None
 
 
+def run_parity_check(params: dict, frame, planes, out) -> dict:
+    """One whole frame through the CPU checker in its own process (oracle/parity_check.py); numpy arrays in, dict out."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    d = Path(tempfile.mkdtemp(prefix="luma_parity_", dir=base))
+    try:
+        (d / "params.json").write_text(json.dumps(params))
+        np.save(d / "in.npy", frame)
+        for i, pl in enumerate(planes):
+            np.save(d / f"p{i}.npy", pl)
+        np.save(d / "out.npy", out)
+        r = subprocess.run([sys.executable, str(ROOT / "oracle" / "parity_check.py"), str(d)], capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else
+                    f"parity_check.py exited with {r.returncode}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def parity_over_ranks(local: dict, dev, world: int) -> dict:
+    """Sum of mismatching plane bytes / frames / pixels, max of ulp over all ranks (one small all_reduce each)."""
+    import torch
+    import torch.distributed as dist
+    failed = 1 if "error" in local else 0
+    sums = torch.tensor([local.get("plane_mismatch_bytes", 0), 0 if failed else 1, local.get("pixels", 0), failed,
+                         0 if local.get("stats_max_equal") in (None, True) else 1], dtype=torch.float64, device=dev)
+    maxs = torch.tensor([local.get("max_ulp", 0), local.get("stats_sum_rel_err") or 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+    res = {"plane_mismatch_bytes": int(sums[0].item()), "max_ulp": int(maxs[0].item()), "frames_checked": int(sums[1].item()),
+           "pixels_checked": int(sums[2].item()), "ranks": world, "ranks_failed": int(sums[3].item()),
+           "checker": local.get("checker"), "whole_frames": True,
+           "what": "one whole frame per rank of the timed batch: planes byte for byte, decoded floats in ulp, vs the CPU checker"}
+    if local.get("stats_max_equal") is not None:
+        res["stats_max_mismatches"] = int(sums[4].item())
+        res["stats_sum_max_rel_err"] = float(maxs[1].item())
+    if failed:
+        res["error_rank_local"] = local["error"]
+    return res
+
+
+def make_transform(cfg: dict, local: int, rank: int, world: int, dev):
+    """DeviceTransform for one configuration; at N > 1 rank 0's host-built quantizer is broadcast (the only collective)."""
+    import lumahdrv_b200 as L
+    from lumahdrv_b200.device import DeviceTransform
+    from lumahdrv_b200.shard import broadcast_quantizer, pack_quantizer, packed_quantizer_size, unpack_quantizer
+    shared_lut = None
+    if world > 1:
+        vec = None
+        if rank == 0:
+            lut = L.build_lut(cfg["ptf"], cfg["bits"], cfg["maxLum"], cfg["minLum"])
+            vec = pack_quantizer(lut, (1 << cfg["cbits"]) - 1, getattr(L, "CS_" + cfg["cs"]), cfg["maxLum"], cfg["minLum"],
+                                 cfg["preScaling"], cfg["profile"], ptf=getattr(L, "PTF_" + cfg["ptf"]))
+        shared_lut = unpack_quantizer(broadcast_quantizer(vec, packed_quantizer_size(cfg["bits"]), dev, src=0))["lut"]
+    return DeviceTransform(local, ptf=cfg["ptf"], ptfBitDepth=cfg["bits"], colorSpace=cfg["cs"], colorBitDepth=cfg["cbits"],
+                           maxLum=cfg["maxLum"], minLum=cfg["minLum"], profile=cfg["profile"], preScaling=cfg["preScaling"],
+                           lut=shared_lut)
+
+
+def synth_frames(F: int, w: int, h: int, first_index: int, dev):
+    """F distinct seeded log-uniform frames, 0.005 .. 1e4 cd/m2 (SURVEY 8d input (2)), generated in HBM."""
+    import torch
+    rgb = torch.empty((F, 3, h, w), dtype=torch.float32, device=dev)
+    for i in range(F):
+        g = torch.Generator(device=dev).manual_seed(0x9E3779B9 + first_index + i)
+        u = torch.rand((3, h, w), generator=g, device=dev, dtype=torch.float32)
+        rgb[i] = 0.005 * torch.pow(torch.tensor(2.0e6, device=dev), u)
+    return rgb
+
+
+def frame_parity(t, cfg: dict, rgb, planes, out, stats, idx: int, dev, world: int) -> dict:
+    """Copy frame `idx` of the batch (input, planes, decoded floats, stats) to the host and check it on the CPU."""
+    import torch
+    torch.cuda.synchronize()
+    params = {"w": cfg["w"], "h": cfg["h"], "profile": cfg["profile"], "ptf": cfg["ptf"], "ptfBitDepth": cfg["bits"],
+              "colorSpace": cfg["cs"], "colorBitDepth": cfg["cbits"], "preScaling": cfg["preScaling"], "maxLum": cfg["maxLum"],
+              "minLum": cfg["minLum"]}
+    if stats is not None:
+        st = t.stats_to_numpy(stats)[idx]
+        params["stats"] = {"sum": float(st["sum"]), "max": float(st["max"]), "min": float(st["min"])}
+    local = run_parity_check(params, rgb[idx].cpu().numpy(), [p[idx].cpu().numpy() for p in planes], out[idx].cpu().numpy())
+    return parity_over_ranks(local, dev, world)
+
+
+def measure_config(name: str, cfg: dict, args, local: int, rank: int, world: int, dev, peak: float) -> dict:
+    """One of cfg2..cfg5: device-resident round trip with the headline's timing code (barrier + synchronize on both sides,
+    CUDA events on the launching stream around every kernel, max over ranks), then a whole-frame parity check."""
+    import torch
+    import torch.distributed as dist
+    from lumahdrv_b200.shard import frame_shard
+    cfg = dict(dict(profile=2, preScaling=1.0, maxLum=1e4, minLum=0.005), **cfg)
+    w, h = cfg["w"], cfg["h"]
+    F = max(cfg["frames"], -(-cfg.get("min_total_frames", 0) // world))
+    mine = frame_shard(F * world, rank, world)
+    t = make_transform(cfg, local, rank, world, dev)
+    rgb = synth_frames(F, w, h, 1000 + mine.start, dev)
+    planes = t.alloc_planes(F, w, h)
+    out = torch.empty_like(rgb)
+    stats = t.alloc_stats(F) if cfg["stats"] else None
+    n_steps, n_warm = max(1, args.config_steps), 3
+    for _ in range(n_warm):
+        t.encode(rgb, planes=planes, stats=stats)
+        t.decode(planes, w, h, out=out)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(n_steps):
+        ev[k][0].record()
+        t.encode(rgb, planes=planes, stats=stats)
+        ev[k][1].record()
+        t.decode(planes, w, h, out=out)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tt = torch.tensor([ev[0][0].elapsed_time(ev[-1][2]), sum(e[0].elapsed_time(e[1]) for e in ev) / n_steps,
+                       sum(e[1].elapsed_time(e[2]) for e in ev) / n_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    tot, enc_ms, dec_ms = (float(v) for v in tt.tolist())
+    px = F * w * h
+    bytes_pass = BYTES_PER_PX_PASS * px
+    res = {"workload": cfg["label"], "frames_per_gpu_per_step": F, "frames_total_per_step": F * world, "steps": n_steps,
+           "warmup": n_warm, "value": world * px * n_steps / (tot / 1e3) / 1e6, "unit": "Mpixels/s",
+           "encode_ms": enc_ms, "decode_ms": dec_ms, "bytes_per_px_per_direction": BYTES_PER_PX_PASS,
+           "encode_gbs": bytes_pass / (enc_ms / 1e3) / 1e9, "decode_gbs": bytes_pass / (dec_ms / 1e3) / 1e9,
+           "frac": bytes_pass / (max(enc_ms, dec_ms) / 1e3) / 1e9 / peak,
+           "round_trip_frac_of_peak": 2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9 / peak,
+           "search": t.quant.search_info()}
+    if stats is not None:
+        st = t.stats_to_numpy(stats)
+        res["stats_frame0"] = {"mean_Y": float(st["sum"][0]) / (w * h), "max_Y": float(st["max"][0]), "min_Y": float(st["min"][0])}
+    if not args.no_parity:
+        res["parity"] = frame_parity(t, cfg, rgb, planes, out, stats, rank % F, dev, world)
+    del rgb, planes, out, stats, t
+    torch.cuda.empty_cache()
+    return res
+
+
 def ours_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import lumahdrv_b200 as L
-    from lumahdrv_b200.device import DeviceTransform
-    from lumahdrv_b200.shard import (broadcast_quantizer, frame_shard, pack_quantizer, packed_quantizer_size,
-                                     unpack_quantizer)
+    from lumahdrv_b200.shard import frame_shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the transform has no CPU fallback)")
@@ -231,29 +416,14 @@ def ours_arm(args):
         affinity = bind_to_gpu_numa(local)
 
     # ---- quantizer: rank 0 builds the LUT with its libm, everyone receives it (the only collective)
-    n_lut = 1 << QUANT["ptfBitDepth"]
-    if world > 1:
-        vec = None
-        if rank == 0:
-            lut = L.build_lut(QUANT["ptf"], QUANT["ptfBitDepth"], QUANT["maxLum"], QUANT["minLum"])
-            vec = pack_quantizer(lut, (1 << QUANT["colorBitDepth"]) - 1, L.CS_LUV, QUANT["maxLum"], QUANT["minLum"],
-                                 QUANT["preScaling"], QUANT["profile"], ptf=L.PTF_PQ)
-        got = unpack_quantizer(broadcast_quantizer(vec, packed_quantizer_size(QUANT["ptfBitDepth"]), dev, src=0))
-        shared_lut = got["lut"]
-    else:
-        shared_lut = None
-    t = DeviceTransform(local, ptf=QUANT["ptf"], ptfBitDepth=QUANT["ptfBitDepth"], colorSpace=QUANT["colorSpace"],
-                        colorBitDepth=QUANT["colorBitDepth"], maxLum=QUANT["maxLum"], minLum=QUANT["minLum"],
-                        profile=QUANT["profile"], preScaling=QUANT["preScaling"], lut=shared_lut)
+    HEAD = dict(w=W, h=H, ptf=QUANT["ptf"], bits=QUANT["ptfBitDepth"], cs=QUANT["colorSpace"], cbits=QUANT["colorBitDepth"],
+                profile=QUANT["profile"], preScaling=QUANT["preScaling"], maxLum=QUANT["maxLum"], minLum=QUANT["minLum"])
+    t = make_transform(HEAD, local, rank, world, dev)
 
     # ---- this rank's shard of the synthetic frame stream (weak scaling: F frames per GPU per step)
     F = args.frames
     mine = frame_shard(F * world, rank, world)
-    rgb = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
-    for i, gidx in enumerate(mine):
-        g = torch.Generator(device=dev).manual_seed(0x9E3779B9 + gidx)
-        u = torch.rand((3, H, W), generator=g, device=dev, dtype=torch.float32)
-        rgb[i] = 0.005 * torch.pow(torch.tensor(2.0e6, device=dev), u)  # log-uniform 0.005 .. 1e4 cd/m2
+    rgb = synth_frames(F, W, H, mine.start, dev)
     planes = t.alloc_planes(F, W, H)
     out = torch.empty_like(rgb)
     stats = t.alloc_stats(F)
@@ -346,9 +516,13 @@ def ours_arm(args):
         copy_gbs = 2 * (1 << 30) / (best / 1e3) / 1e9
         del src_c, dst_c
 
-    # sanity: the timed work really produced the round trip (compare one frame with the input scale)
+    # ---- parity of the benchmark's OWN data, outside the timed region: every rank has the CPU checker redo one whole
+    # frame of the batch the timed steps just produced (input -> planes -> decoded floats, plus the Y statistics)
     st = t.stats_to_numpy(stats)
     assert np.all(np.isfinite(st["sum"])) and np.all(st["sum"] > 0)
+    parity = None
+    if not args.no_parity:
+        parity = frame_parity(t, HEAD, rgb, planes, out, stats, (rank * 5 + 3) % F, dev, world)
 
     # ---- end to end through the host-pointer C ABI, pinned host memory, copies inside the timed region
     e2e = None
@@ -391,6 +565,7 @@ def ours_arm(args):
         h_outs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
         free_q, full_q = queue.Queue(), queue.Queue()
         errors = []
+        last_slot = [0]
 
         def enc_thread(nframes):
             try:
@@ -411,6 +586,7 @@ def ours_arm(args):
                         return
                     dec.m_frame = h_outs[k & 1]
                     dec.decode(slots[s], W, H)                # H2D 3 B/px, kernel, D2H 12 B/px
+                    last_slot[0] = s
                     free_q.put(s)
                     k += 1
             except Exception as e:  # noqa: BLE001
@@ -447,6 +623,15 @@ def ours_arm(args):
         # the last decoded frame must be the round trip of its input (spot check, outside the timed region)
         chk = t.decode(t.encode(rgb[(Fe * e2e_steps - 1) % Fe][None]), W, H)[0].cpu().numpy()
         assert np.array_equal(chk.view(np.uint32), h_outs[(Fe * e2e_steps - 1) & 1].view(np.uint32)), "e2e result differs"
+        # ... and the CPU checker redoes that frame from the host buffers the C ABI filled (planes + decoded floats)
+        e2e_parity = None
+        if not args.no_parity:
+            prm = {"w": W, "h": H, "profile": QUANT["profile"], "ptf": QUANT["ptf"], "ptfBitDepth": QUANT["ptfBitDepth"],
+                   "colorSpace": QUANT["colorSpace"], "colorBitDepth": QUANT["colorBitDepth"], "preScaling": QUANT["preScaling"],
+                   "maxLum": QUANT["maxLum"], "minLum": QUANT["minLum"],
+                   "stats": {k: float(enc.last_stats[k]) for k in ("sum", "max", "min")}}
+            e2e_parity = parity_over_ranks(run_parity_check(prm, np_in[(Fe * e2e_steps - 1) % Fe], slots[last_slot[0]],
+                                                            h_outs[(Fe * e2e_steps - 1) & 1]), dev, world)
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -454,9 +639,24 @@ def ours_arm(args):
         plane_bytes = sum(pw * ph * 2 for pw, ph in L.plane_dims(W, H, QUANT["profile"]))
         e2e = {"value": world * Fe * W * H * e2e_steps / dt / 1e6, "unit": "Mpixels/s",
                "h2d_bytes_per_step": Fe * (12 * W * H + plane_bytes), "d2h_bytes_per_step": Fe * (12 * W * H + plane_bytes),
-               "steps": e2e_steps, "frames_per_step": Fe, "gpu_launches": e2e_launches,
+               "steps": e2e_steps, "frames_per_step": Fe, "gpu_launches": e2e_launches, "parity": e2e_parity,
                "api": "LumaEncoder.encode / LumaDecoder.decode -> lumacu_encode + lumacu_decode (host pointers, pinned), "
                       "encoder and decoder objects on two host threads (frame i+1 encodes while frame i decodes)"}
+
+    # ---- the other BASELINE configurations (a few steps each, same timing code, own parity check)
+    configs = None
+    if not args.no_configs:
+        del rgb, planes, out
+        torch.cuda.empty_cache()
+        peak_c, _ = measured_peak_gbs()
+        configs = {}
+        for name, cfg in OTHER_CONFIGS.items():
+            try:
+                configs[name] = measure_config(name, cfg, args, local, rank, world, dev, peak_c)
+            except Exception as e:  # noqa: BLE001 -- a failing side configuration must not lose the headline line
+                if world > 1:
+                    raise
+                configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -469,10 +669,7 @@ def ours_arm(args):
             "metric": "Mpixels/s encode+decode (PQ Lu'v' 4K float32)", "value": value, "unit": "Mpixels/s",
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F,
-                       "input": "seeded log-uniform noise 0.005..1e4 cd/m2, distinct per frame",
-                       "l2": f"inputs larger than L2: {F * (12 + 3 + 12) * W * H / 1e6:.0f} MB touched per step per GPU vs 126 MB L2",
-                       "parallelism": f"frame shards x{world}, LUT broadcast only"},
+            "config": config_dict(world, F),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                          "traffic_source": (f"ncu --set full capture {traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
@@ -491,6 +688,10 @@ def ours_arm(args):
         }
         if e2e:
             line["e2e"] = e2e
+        if parity:
+            line["parity"] = parity
+        if configs:
+            line["configs"] = configs
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": "Mpixels/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                     "sample": cpu["sample"], "per_core_mpx_s": cpu["per_core_mpx_s"]}

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define LUMACU_VERSION 100 /* 0.1.0 */
+#define LUMACU_VERSION 200 /* 0.2.0 */
 
 typedef enum lumacu_status {
     LUMACU_OK = 0,
@@ -176,6 +176,17 @@ int lumacu_plan_buckets(const uint32_t *thr_keys, uint32_t n_thr, uint32_t *shif
 int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t lut_len,
                          uint32_t max_val_color, int color_space, float max_lum);
 
+/* Single-process multi-GPU: every context in ctxs[0..n) receives ctxs[root]'s quantizer.  The host-side derivation
+ * (LUT, exact decision thresholds, search tables) is NOT repeated: the root's device tables travel to each peer in one
+ * peer-to-peer copy (NVLink / NVSwitch between B200s), so all GPUs search with bit-identical tables; call it again
+ * after the root's table changed, e.g. when the decoder overlaid attachment 434 (src/luma_decoder.cpp:121-122).
+ * The reference has one quantizer per process and nothing to replace here; processes on different GPUs exchange
+ * lumacu_metadata_pack blobs instead (NCCL broadcast, lumahdrv_b200/shard.py). */
+int lumacu_broadcast_quantizer(lumacu_ctx *const ctxs[], int n, int root);
+/* Host copy of the quantizer a context currently holds; any output pointer may be NULL. */
+int lumacu_get_quantizer(const lumacu_ctx *ctx, float *lut_out, size_t cap, uint32_t *lut_len,
+                         uint32_t *max_val_color, int *color_space, float *max_lum);
+
 /* ---- whole-frame transform, host memory ------------------------------------- */
 /* LumaEncoder::encode minus run() (include/luma/luma_encoder.h:142-148):
  * rgb (3*w*h f32, NOT modified unless write_back != 0, in which case it
@@ -191,6 +202,24 @@ int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profi
  * planes -> rgb (3*w*h f32). */
 int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
                   uint32_t w, uint32_t h, int profile, float pre_scaling, float *rgb);
+
+/* Asynchronous forms of the two calls above: the copies and the kernel are queued on the context's streams and the
+ * call returns at once, so that the host thread can do something else meanwhile -- run libvpx on the previous
+ * frame's planes (what LumaEncoder::run does between two encode() calls, include/luma/luma_encoder.h:142-148), or
+ * drive the next GPU.  ONE call in flight per context: any later host-pointer call on the same context first
+ * completes it.
+ *   lumacu_wait_input  returns when the call's INPUT buffer (rgb for encode -- unless write_back -- / planes for
+ *                      decode) has been read completely and may be reused;
+ *   lumacu_wait        returns when the results are in host memory (and *stats is filled);
+ *   lumacu_pending     1 while a call is in flight. */
+int lumacu_encode_async(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile,
+                        float pre_scaling, uint8_t *const planes[3], const int32_t strides[3],
+                        int write_back, lumacu_frame_stats *stats);
+int lumacu_decode_async(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
+                        uint32_t w, uint32_t h, int profile, float pre_scaling, float *rgb);
+int lumacu_wait_input(lumacu_ctx *ctx);
+int lumacu_wait(lumacu_ctx *ctx);
+int lumacu_pending(const lumacu_ctx *ctx);
 
 /* The two halves of the reference's unfused path, for callers that use them separately:
  * lumacu_quantize_planes = LumaEncoder::setChannels (src/luma_encoder.cpp:196-201,260-317): `frame` is
@@ -254,6 +283,12 @@ typedef struct lumacu_display_params {
     float user_scaling; /* lumaplay's userScaling, 1 = none */
     int do_tmo;         /* sigmoid tone curve on/off */
     int ldr_sim;        /* 8-bit LDR simulation on/off */
+    int filter;         /* 0: sample like the CPU decoder (nearest-neighbour chroma, exact LUT entries, exact
+                         * LumaDecoder::decode arithmetic); 1: sample like the player itself -- its textures are
+                         * GL_LINEAR, CLAMP_TO_EDGE (lumaplay.cpp:258-259), so at 1:1 scale 4:2:0 chroma is bilinear
+                         * with weights 1/4 : 3/4 per direction and the luminance fetch from the one-short LUT
+                         * texture (lumaplay.cpp:371) is the mean of lut[code-1] and lut[code]; the rest of the
+                         * shader in plain fp32 (PQ with its built-in L = 10000) */
 } lumacu_display_params;
 int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
                    uint32_t h, int profile, float pre_scaling, const lumacu_display_params *params,
@@ -273,6 +308,17 @@ int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, uint32_t h,
  * reference ("luminance only frames not yet supported"). */
 int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba_half, uint32_t w, uint32_t h, int channels,
                                   float *d_rgb, void *stream);
+
+/* PfsInterface::readFrame / writeFrame (src/pfs_interface.cpp:57-113, :115-152) minus the stream parsing: a PFS frame
+ * carries X, Y, Z as three separate w*h float arrays; the reference runs pfstools' pfs::transformColorSpace
+ * (CS_XYZ -> CS_RGB at :84, CS_RGB -> CS_XYZ at :140) and copies the channels into / out of the planar frame.
+ * pfstools is not part of the reference tree ("parity unpinned"): its D65 matrices carry the same nine constants as
+ * the reference's own xyz2rgbMat / rgb2xyzMat (include/luma/luma_quantizer.h:79-87), applied per pixel as
+ * m0*a + m1*b + m2*c in float without clamping -- which is what these kernels do.  d_rgb is 3*w*h floats. */
+int lumacu_pfs_xyz_to_frame_dev(lumacu_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, uint32_t w,
+                                uint32_t h, float *d_rgb, void *stream);
+int lumacu_frame_to_pfs_xyz_dev(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_t h, float *d_x, float *d_y,
+                                float *d_z, void *stream);
 
 /* ---- introspection (used by bench.py / tests) -------------------------------- */
 /* Number of kernels this context has launched so far. */

@@ -40,7 +40,8 @@ class FrameStats(C.Structure):
 
 class DisplayParams(C.Structure):
     """lumacu_display_params (include/lumacu.h)."""
-    _fields_ = [("exposure", C.c_float), ("gamma", C.c_float), ("user_scaling", C.c_float), ("do_tmo", C.c_int), ("ldr_sim", C.c_int)]
+    _fields_ = [("exposure", C.c_float), ("gamma", C.c_float), ("user_scaling", C.c_float), ("do_tmo", C.c_int), ("ldr_sim", C.c_int),
+                ("filter", C.c_int)]
 
 
 class Metadata(C.Structure):
@@ -83,6 +84,15 @@ SIGNATURES = {
     "lumacu_plan_buckets": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "lumacu_set_quantizer": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float]),
+    "lumacu_broadcast_quantizer": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "lumacu_get_quantizer": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_float)]),
+    "lumacu_encode_async": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
+                                      C.POINTER(FrameStats)]),
+    "lumacu_decode_async": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
+    "lumacu_wait_input": (C.c_int, [_P]),
+    "lumacu_wait": (C.c_int, [_P]),
+    "lumacu_pending": (C.c_int, [_P]),
     "lumacu_encode": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
                                 C.POINTER(FrameStats)]),
     "lumacu_decode": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
@@ -91,6 +101,8 @@ SIGNATURES = {
                                      C.c_int32, C.c_uint32, _P, C.c_size_t, _P]),
     "lumacu_test_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P]),
     "lumacu_half_rgba_to_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
+    "lumacu_pfs_xyz_to_frame_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
+    "lumacu_frame_to_pfs_xyz_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "lumacu_set_host_bands": (C.c_int, [_P, C.c_int]),
     "lumacu_host_register": (C.c_int, [_P, C.c_size_t]),
     "lumacu_host_unregister": (C.c_int, [_P]),

@@ -49,5 +49,8 @@ void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, cons
 const void *quantize_kernel_ptr();
 void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
 void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);
+void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,
+                         float *o0, float *o1, float *o2, size_t n);
+void launch_display_linear(unsigned blocks, unsigned n_frames, cudaStream_t st, const DecArgs &a, int cs, int sub, int bytes);
 
 } // namespace lumacu

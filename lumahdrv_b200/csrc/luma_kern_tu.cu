@@ -96,6 +96,20 @@ void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgb
 {
     half_rgba_to_frame_kernel<<<blocks, kThreads, 0, st>>>((const uint2 *)rgba, rgb, n, mode);
 }
+
+void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,
+                         float *o0, float *o1, float *o2, size_t n)
+{
+    if (to_rgb)
+        pfs_channels_kernel<true><<<blocks, kThreads, 0, st>>>(a0, a1, a2, o0, o1, o2, n);
+    else
+        pfs_channels_kernel<false><<<blocks, kThreads, 0, st>>>(a0, a1, a2, o0, o1, o2, n);
+}
+
+void launch_display_linear(unsigned blocks, unsigned n_frames, cudaStream_t st, const DecArgs &a, int cs, int sub, int bytes)
+{
+    display_linear_kernel<<<dim3(blocks, n_frames), kThreads, 0, st>>>(a, cs, sub, bytes);
+}
 #endif
 
 #else /* LUMA_TU_FAST */

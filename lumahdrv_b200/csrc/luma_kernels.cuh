@@ -692,6 +692,141 @@ __global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint
     }
 }
 
+/* PfsInterface::readFrame / writeFrame (src/pfs_interface.cpp:57-113, :115-152): a PFS stream carries the colour
+ * channels X, Y, Z as three separate float arrays; the reference converts them with pfstools'
+ * pfs::transformColorSpace(CS_XYZ -> CS_RGB) (:84) -- resp. CS_RGB -> CS_XYZ (:140) -- and memcpy's the three channels
+ * into the LumaFrame planes (:100-102).  pfstools (libpfs, src/pfs/colorspace.cpp, NOT part of the reference tree:
+ * "parity unpinned") multiplies every pixel by its D65 matrices xyz2rgbD65Mat / rgb2xyzD65Mat, which hold the same
+ * nine constants as the reference's own xyz2rgbMat / rgb2xyzMat (include/luma/luma_quantizer.h:79-87), evaluated
+ * m0*a + m1*b + m2*c left to right in float, no clamp.  TO_RGB selects the direction. */
+template <bool TO_RGB>
+__global__ void __launch_bounds__(kThreads) pfs_channels_kernel(const float *__restrict__ a0, const float *__restrict__ a1,
+                                                                const float *__restrict__ a2, float *__restrict__ o0,
+                                                                float *__restrict__ o1, float *__restrict__ o2, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float a = __ldcs(a0 + i), b = __ldcs(a1 + i), c = __ldcs(a2 + i);
+        float x, y, z;
+        if (TO_RGB) {
+            x = dot3(LUMA_I00, LUMA_I01, LUMA_I02, a, b, c);
+            y = dot3(LUMA_I10, LUMA_I11, LUMA_I12, a, b, c);
+            z = dot3(LUMA_I20, LUMA_I21, LUMA_I22, a, b, c);
+        } else {
+            x = dot3(LUMA_M00, LUMA_M01, LUMA_M02, a, b, c);
+            y = dot3(LUMA_M10, LUMA_M11, LUMA_M12, a, b, c);
+            z = dot3(LUMA_M20, LUMA_M21, LUMA_M22, a, b, c);
+        }
+        __stcs(o0 + i, x);
+        __stcs(o1 + i, y);
+        __stcs(o2 + i, z);
+    }
+}
+
+/* ---- the player's own sampling (lumacu_display_params.filter = 1) --------------------------------------------
+ * The reference's player draws the decoder's planes as GL_LINEAR textures (lumaplay.cpp:258-259 sets MIN/MAG filter
+ * GL_LINEAR and CLAMP_TO_EDGE for every texture, the LUT included) and dequantises in the fragment shader
+ * (src/lumaplay_dequantizer.frag:70-157).  At 1:1 scale that means, for output pixel (x, y):
+ *   - plane 0 is sampled at its own texel centres: the code itself;
+ *   - a half-resolution chroma plane is sampled at u = x/2 - 1/4, v = y/2 - 1/4 (texel units): bilinear weights 1/4 : 3/4
+ *     towards the nearer chroma sample in each direction, clamped at the plane's edges;
+ *   - the LUT texture is uploaded with getSize() = maxVal texels (one short, lumaplay.cpp:371) and fetched at
+ *     code / maxVal: texel coordinate code - 1/2, i.e. the MEAN of lut[code-1] and lut[code] (lut[0] for code 0,
+ *     lut[maxVal-1] for code >= maxVal);
+ *   - chroma is code / maxValColor without the CPU path's 1e-10 floor; the PQ used for YCbCr has L = 10000 built in.
+ * One thread per output pixel; plain fp32 like the shader (approximate by nature). */
+__device__ __forceinline__ float disp_code(const uint8_t *pl, int32_t stride, int bytes, uint32_t x, uint32_t y)
+{
+    const uint8_t *p = pl + (size_t)y * stride + (size_t)x * bytes;
+    return bytes == 2 ? (float)(p[0] | (p[1] << 8)) : (float)p[0];
+}
+__device__ __forceinline__ float disp_lut_linear(const float *lut, uint32_t max_val, float code)
+{
+    /* texture1D(texM, clamp(code, 0, maxVal) / maxVal) on a maxVal-texel GL_LINEAR, CLAMP_TO_EDGE texture */
+    const float t = fminf(fmaxf(code, 0.0f), (float)max_val) - 0.5f;
+    const float fl = floorf(t), f = t - fl;
+    const int last = (int)max_val - 1;
+    const int i0 = min(max((int)fl, 0), last), i1 = min(max((int)fl + 1, 0), last);
+    return lut[i0] + f * (lut[i1] - lut[i0]);
+}
+__device__ __forceinline__ float disp_pq(float val, bool encode)
+{
+    const float L = 10000.0f, m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
+    if (encode) {
+        const float Lp = powf(val / L, n);
+        return powf((c1 + c2 * Lp) / (1.0f + c3 * Lp), m);
+    }
+    const float Vp = powf(val, 1.0f / m);
+    return L * powf(fmaxf(0.0f, Vp - c1) / (c2 - c3 * Vp), 1.0f / n);
+}
+__global__ void __launch_bounds__(kThreads) display_linear_kernel(const DecArgs a, int cs, int sub, int bytes)
+{
+    const size_t n = (size_t)a.w * a.h;
+    const uint32_t frame = blockIdx.y;
+    const uint8_t *pl0 = a.plane[0] + (size_t)frame * a.plane_frame_stride[0];
+    const uint8_t *pl1 = a.plane[1] + (size_t)frame * a.plane_frame_stride[1];
+    const uint8_t *pl2 = a.plane[2] + (size_t)frame * a.plane_frame_stride[2];
+    uint8_t *out = a.rgba + (size_t)frame * a.rgba_frame_stride;
+    const uint32_t cw = sub ? (a.w + 1) >> 1 : a.w, chh = sub ? (a.h + 1) >> 1 : a.h;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const uint32_t y = (uint32_t)(i / a.w), x = (uint32_t)(i - (size_t)y * a.w);
+        float c0 = disp_code(pl0, a.stride[0], bytes, x, y), c1, c2;
+        if (sub) {
+            const float u = 0.5f * (float)x - 0.25f, v = 0.5f * (float)y - 0.25f;
+            const float uf = floorf(u), vf = floorf(v), fx = u - uf, fy = v - vf;
+            const uint32_t x0 = (uint32_t)max((int)uf, 0), x1 = min((uint32_t)((int)uf + 1), cw - 1);
+            const uint32_t y0 = (uint32_t)max((int)vf, 0), y1 = min((uint32_t)((int)vf + 1), chh - 1);
+            const float p00 = disp_code(pl1, a.stride[1], bytes, x0, y0), p10 = disp_code(pl1, a.stride[1], bytes, x1, y0);
+            const float p01 = disp_code(pl1, a.stride[1], bytes, x0, y1), p11 = disp_code(pl1, a.stride[1], bytes, x1, y1);
+            const float q00 = disp_code(pl2, a.stride[2], bytes, x0, y0), q10 = disp_code(pl2, a.stride[2], bytes, x1, y0);
+            const float q01 = disp_code(pl2, a.stride[2], bytes, x0, y1), q11 = disp_code(pl2, a.stride[2], bytes, x1, y1);
+            const float pa = p00 + fx * (p10 - p00), pb = p01 + fx * (p11 - p01);
+            const float qa = q00 + fx * (q10 - q00), qb = q01 + fx * (q11 - q01);
+            c1 = pa + fy * (pb - pa);
+            c2 = qa + fy * (qb - qa);
+        } else {
+            c1 = disp_code(pl1, a.stride[1], bytes, x, y);
+            c2 = disp_code(pl2, a.stride[2], bytes, x, y);
+        }
+        c0 = disp_lut_linear(a.q.lut, a.q.max_val, c0);
+        if (cs == CS_RGB || cs == CS_XYZ) {
+            c1 = disp_lut_linear(a.q.lut, a.q.max_val, c1);
+            c2 = disp_lut_linear(a.q.lut, a.q.max_val, c2);
+        } else {
+            c1 = c1 / a.q.max_val_color_f;
+            c2 = c2 / a.q.max_val_color_f;
+        }
+        float R, G, B;
+        if (cs == CS_LUV) {
+            const float L = c0, u = c1 * 255.0f / 410.0f, v = c2 * 255.0f / 410.0f;
+            const float den = 6.0f * u - 16.0f * v + 12.0f;
+            const float xx = 9.0f * u / den, yy = 4.0f * v / den;
+            const float Y = fmaxf(fminf(L, 100000000.0f), 0.0001f);
+            const float X = fmaxf(fminf(xx / yy * L, 100000000.0f), 0.0001f);
+            const float Z = fmaxf(fminf((1.0f - xx - yy) / yy * L, 100000000.0f), 0.0001f);
+            R = LUMA_I00 * X + LUMA_I01 * Y + LUMA_I02 * Z;
+            G = LUMA_I10 * X + LUMA_I11 * Y + LUMA_I12 * Z;
+            B = LUMA_I20 * X + LUMA_I21 * Y + LUMA_I22 * Z;
+        } else if (cs == CS_RGB) {
+            R = c0, G = c1, B = c2;
+        } else if (cs == CS_YCBCR) {
+            float yv = disp_pq(c0, true);
+            yv = (255.0f * yv - 16.0f) / 219.0f;
+            B = yv + 1.8814f * (255.0f * c1 - 128.0f) / 224.0f;
+            R = yv + 1.4746f * (255.0f * c2 - 128.0f) / 224.0f;
+            G = (yv - 0.2627f * R - 0.0593f * B) / 0.6780f;
+            R = disp_pq(fmaxf(0.0f, fminf(1.0f, R)), false);
+            G = disp_pq(fmaxf(0.0f, fminf(1.0f, G)), false);
+            B = disp_pq(fmaxf(0.0f, fminf(1.0f, B)), false);
+        } else {
+            R = LUMA_I00 * c0 + LUMA_I01 * c1 + LUMA_I02 * c2;
+            G = LUMA_I10 * c0 + LUMA_I11 * c1 + LUMA_I12 * c2;
+            B = LUMA_I20 * c0 + LUMA_I21 * c1 + LUMA_I22 * c2;
+        }
+        const uint32_t px = display_unorm8(R, a) | (display_unorm8(G, a) << 8) | (display_unorm8(B, a) << 16) | 0xff000000u;
+        *reinterpret_cast<uint32_t *>(out + (size_t)y * a.rgba_pitch + (size_t)x * 4) = px;
+    }
+}
+
 #endif /* LUMA_TU_ELEMENTWISE */
 
 } // namespace lumacu

@@ -102,7 +102,9 @@ struct lumacu_ctx {
     int color_space = 0;
     QuantDev q{};
     std::vector<float> h_lut;
-    DeviceBuffer d_tables; /* lut | thr | bucket */
+    DeviceBuffer d_tables; /* lut | thr | bucket | ctab | dtab | ylut */
+    size_t tables_bytes = 0; /* bytes of d_tables in use (what lumacu_broadcast_quantizer copies to the peers) */
+    float max_lum = 0.0f;
     size_t smem_enc = 0, smem_dec = 0;
     size_t smem_dec_fast = 0; /* lut + chroma table; 0 = fast decode unavailable */
     bool fast_enc_ok = false;
@@ -117,7 +119,14 @@ struct lumacu_ctx {
     int host_bands = 0;               /* tuning: number of row bands per host-pointer call (0 = automatic) */
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
+    /* asynchronous host-pointer call in flight (lumacu_encode_async / lumacu_decode_async -> lumacu_wait) */
+    bool pending = false;
+    lumacu_frame_stats *pending_stats = nullptr; /* caller's stats to fill at lumacu_wait (NULL = none) */
+    int pending_bands = 0;
+    cudaEvent_t ev_input = nullptr; /* recorded after the last H2D copy of the call: the caller's input is reusable */
 };
+
+static int finish_pending(lumacu_ctx *ctx);
 
 namespace {
 
@@ -514,12 +523,16 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
         return LUMACU_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_out)
+        cudaStreamSynchronize(ctx->s_out); /* an asynchronous call the caller never waited for */
     for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
                             &ctx->d_aux})
         if (b->p)
             cudaFree(b->p);
     if (ctx->h_pin)
         cudaFreeHost(ctx->h_pin);
+    if (ctx->ev_input)
+        cudaEventDestroy(ctx->ev_input);
     for (cudaEvent_t ev : ctx->ev_in)
         cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_k)
@@ -543,7 +556,7 @@ try {
         return LUMACU_ERR_INVALID_ARGUMENT;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return LUMACU_OK;
+    return finish_pending(ctx);
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
@@ -613,6 +626,8 @@ try {
     if (max_val_color < 1 || max_val_color > 65535u)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_quantizer: max_val_color %u not in [1,65535]", max_val_color);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (int rcp = finish_pending(ctx))
+        return rcp;
 
     const uint32_t max_val = lut_len - 1;
     std::vector<uint32_t> thr(max_val ? max_val : 1);
@@ -796,11 +811,94 @@ try {
     ctx->smem_dec_fast = smem_dec_fast;
 
     ctx->q = q;
+    ctx->tables_bytes = total;
+    ctx->max_lum = max_lum;
     ctx->smem_enc = smem_enc;
     ctx->smem_dec = smem_dec;
     ctx->color_space = color_space;
     ctx->h_lut.assign(lut, lut + lut_len);
     ctx->configured = true;
+    return LUMACU_OK;
+}
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
+/* Single-process multi-GPU: every context receives ctxs[root]'s quantizer -- the host LUT and scalars, and the DEVICE
+ * tables (LUT, decision thresholds, bucket heads, direct search table, chroma / y' tables) by one peer-to-peer copy per
+ * destination (NVLink/NVSwitch when the devices are peers, staged by the driver otherwise), so that the host-side
+ * derivation runs once and every GPU searches with bit-identical tables.  Replaces nothing in the reference (it has
+ * one quantizer per process); it is the in-process form of the LUT broadcast SURVEY 8e asks for.  Processes on
+ * different GPUs exchange lumacu_metadata_pack blobs instead (lumahdrv_b200/shard.py: NCCL broadcast). */
+extern "C" int lumacu_broadcast_quantizer(lumacu_ctx *const ctxs[], int n, int root)
+try {
+    if (!ctxs || n < 1 || root < 0 || root >= n)
+        return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_broadcast_quantizer: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i])
+            return fail(nullptr, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_broadcast_quantizer: ctxs[%d] is NULL", i);
+    lumacu_ctx *src = ctxs[root];
+    if (!src->configured)
+        return fail(src, LUMACU_ERR_NOT_CONFIGURED, "lumacu_broadcast_quantizer: the root context has no quantizer");
+    const unsigned char *src_base = (const unsigned char *)src->d_tables.p;
+    CU_TRY(src, cudaSetDevice(src->device));
+    CU_TRY(src, cudaDeviceSynchronize()); /* the root's tables are complete and not being replaced */
+    for (int i = 0; i < n; i++) {
+        lumacu_ctx *dst = ctxs[i];
+        if (dst == src)
+            continue;
+        CU_TRY(dst, cudaSetDevice(dst->device));
+        int rc = finish_pending(dst);
+        if (rc || (rc = reserve(dst, dst->d_tables, src->tables_bytes)))
+            return rc;
+        CU_TRY(dst, cudaDeviceSynchronize()); /* launches on the destination may still read its old tables */
+        if (dst->device == src->device)
+            CU_TRY(dst, cudaMemcpyAsync(dst->d_tables.p, src_base, src->tables_bytes, cudaMemcpyDeviceToDevice, dst->stream));
+        else
+            CU_TRY(dst, cudaMemcpyPeerAsync(dst->d_tables.p, dst->device, src_base, src->device, src->tables_bytes, dst->stream));
+        CU_TRY(dst, cudaStreamSynchronize(dst->stream));
+        /* same table layout, other base address */
+        QuantDev q = src->q;
+        unsigned char *dst_base = (unsigned char *)dst->d_tables.p;
+        auto rebase = [&](const void *p) -> const void * {
+            return p ? (const void *)(dst_base + ((const unsigned char *)p - src_base)) : nullptr;
+        };
+        q.lut = (const float *)rebase(q.lut);
+        q.thr = (const uint32_t *)rebase(q.thr);
+        q.bucket = (const uint16_t *)rebase(q.bucket);
+        q.ctab = (const float *)rebase(q.ctab);
+        q.dtab = (const uint32_t *)rebase(q.dtab);
+        q.ylut = (const float *)rebase(q.ylut);
+        dst->q = q;
+        dst->tables_bytes = src->tables_bytes;
+        dst->max_lum = src->max_lum;
+        dst->color_space = src->color_space;
+        dst->h_lut = src->h_lut;
+        dst->smem_enc = src->smem_enc;
+        dst->smem_dec = src->smem_dec;
+        dst->smem_dec_fast = src->smem_dec_fast;
+        dst->fast_enc_ok = src->fast_enc_ok;
+        dst->configured = true;
+    }
+    return LUMACU_OK;
+}
+LUMACU_CATCH(nullptr)
+
+/* Host copy of the quantizer a context holds (what lumacu_set_quantizer / lumacu_broadcast_quantizer left there):
+ * lut_out receives up to `cap` floats; *lut_len, *max_val_color, *color_space, *max_lum may be NULL. */
+extern "C" int lumacu_get_quantizer(const lumacu_ctx *ctx, float *lut_out, size_t cap, uint32_t *lut_len, uint32_t *max_val_color,
+                                    int *color_space, float *max_lum)
+try {
+    if (!ctx || !ctx->configured)
+        return LUMACU_ERR_NOT_CONFIGURED;
+    if (lut_len)
+        *lut_len = (uint32_t)ctx->h_lut.size();
+    if (max_val_color)
+        *max_val_color = ctx->q.max_val_color;
+    if (color_space)
+        *color_space = ctx->color_space;
+    if (max_lum)
+        *max_lum = ctx->max_lum;
+    if (lut_out)
+        memcpy(lut_out, ctx->h_lut.data(), std::min(cap, ctx->h_lut.size()) * sizeof(float));
     return LUMACU_OK;
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
@@ -1185,6 +1283,15 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
         }
         vec = vec && aligned(a.rgba, 16) && (a.rgba_frame_stride % 16 == 0);
     }
+    if (opt.display && opt.display->filter == 1) { /* the player's own GL_LINEAR sampling: one thread per output pixel */
+        const size_t npx = (size_t)w * h;
+        const unsigned blocks = (unsigned)std::min<size_t>((npx + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+        launch_display_linear(blocks, n_frames, st, a, ctx->color_space, sub ? 1 : 0, bytes);
+        CU_TRY(ctx, cudaGetLastError());
+        ctx->last_fast = false;
+        ctx->launches++;
+        return LUMACU_OK;
+    }
     /* the tuned kernel walks whole 2-row tiles: odd heights (legal for 4:4:4 decode) take the generic kernel */
     if (vec && (h % 2 == 0) && small32 && ctx->smem_dec_fast && !ctx->force_generic && !opt.passthrough && !opt.display) {
         fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
@@ -1229,6 +1336,8 @@ try {
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: rgba_pitch must be a multiple of 4 and >= 4*w");
     if (!(params->gamma > 0.0f) || !(params->user_scaling > 0.0f))
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: gamma and user_scaling must be positive");
+    if (params->filter != 0 && params->filter != 1)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: filter %d not in {0,1}", params->filter);
     if (!aligned(d_rgba, 4))
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_display_dev: rgba must be 4-byte aligned");
     LaunchOpts opt;
@@ -1280,6 +1389,44 @@ try {
     return LUMACU_OK;
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
+/* PFS frame source / sink (src/pfs_interface.cpp:57-113, :115-152): three separate channel arrays <-> planar frame */
+static int pfs_channels(lumacu_ctx *ctx, bool to_rgb, const float *a0, const float *a1, const float *a2, float *o0, float *o1,
+                        float *o2, uint32_t w, uint32_t h, void *stream, const char *who)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!a0 || !a1 || !a2 || !o0 || !w || !h)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "%s: NULL pointer or empty size", who);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t n = (size_t)w * h;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    launch_pfs_channels(to_rgb, blocks, st, a0, a1, a2, o0, o1, o2, n);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+
+extern "C" int lumacu_pfs_xyz_to_frame_dev(lumacu_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, uint32_t w,
+                                           uint32_t h, float *d_rgb, void *stream)
+try {
+    const size_t n = (size_t)w * h;
+    return pfs_channels(ctx, true, d_x, d_y, d_z, d_rgb, d_rgb ? d_rgb + n : nullptr, d_rgb ? d_rgb + 2 * n : nullptr, w, h, stream,
+                        "lumacu_pfs_xyz_to_frame_dev");
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_frame_to_pfs_xyz_dev(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_t h, float *d_x, float *d_y,
+                                           float *d_z, void *stream)
+try {
+    const size_t n = (size_t)w * h;
+    if (!d_y || !d_z)
+        return ctx ? fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_frame_to_pfs_xyz_dev: NULL pointer") : LUMACU_ERR_INVALID_ARGUMENT;
+    return pfs_channels(ctx, false, d_rgb, d_rgb ? d_rgb + n : nullptr, d_rgb ? d_rgb + 2 * n : nullptr, d_x, d_y, d_z, w, h, stream,
+                        "lumacu_frame_to_pfs_xyz_dev");
+}
+LUMACU_CATCH(ctx)
 
 extern "C" int lumacu_transform_color_space_dev(lumacu_ctx *ctx, float *d_frame, uint32_t w, uint32_t h, int to_cs, float sc,
                                                 void *stream)
@@ -1420,9 +1567,44 @@ inline uint32_t band_row(uint32_t h, int nb, int b) /* first row of band b; even
 
 } // namespace
 
+/* Completes the asynchronous host-pointer call in flight on this context, if any: waits for its last D2H copy and
+ * folds the per-band statistics into the caller's lumacu_frame_stats.  Every host-pointer entry point starts with it
+ * (the staging buffers and streams are per context: ONE call in flight). */
+static int finish_pending(lumacu_ctx *ctx)
+{
+    if (!ctx->pending)
+        return LUMACU_OK;
+    ctx->pending = false;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
+    if (ctx->pending_stats) {
+        const lumacu_frame_stats *hs = (const lumacu_frame_stats *)ctx->h_pin;
+        lumacu_frame_stats *stats = ctx->pending_stats;
+        *stats = hs[0];
+        for (int b = 1; b < ctx->pending_bands; b++) {
+            stats->sum += hs[b].sum;
+            stats->max = fmaxf(stats->max, hs[b].max);
+            stats->min = fminf(stats->min, hs[b].min);
+        }
+        ctx->pending_stats = nullptr;
+    }
+    return LUMACU_OK;
+}
+
+static int ensure_async_state(lumacu_ctx *ctx)
+{
+    if (!ctx->h_pin) {
+        CU_TRY(ctx, cudaHostAlloc(&ctx->h_pin, 4096, cudaHostAllocPortable));
+        ctx->h_pin_cap = 4096;
+    }
+    if (!ctx->ev_input)
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_input, cudaEventDisableTiming));
+    return LUMACU_OK;
+}
+
 static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
                        uint8_t *const planes[3], const int32_t strides[3], int write_back, lumacu_frame_stats *stats,
-                       bool passthrough)
+                       bool passthrough, bool async = false)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
@@ -1434,6 +1616,8 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
     if (rc)
         return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
+        return rc;
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
@@ -1462,6 +1646,8 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
         CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb + (size_t)y0 * w, npx * 4, rgb + (size_t)y0 * w, npx * 4, (size_t)rows * w * 4, 3,
                                       cudaMemcpyHostToDevice, ctx->s_in));
         CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        if (b == nb - 1 && !write_back)
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_input, ctx->s_in)); /* the caller's frame has been read completely */
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         const uint32_t cy0 = sub ? y0 >> 1 : y0;
         uint8_t *bp[3] = {dp[0] + (size_t)y0 * dstride[0], dp[1] + (size_t)cy0 * dstride[1], dp[2] + (size_t)cy0 * dstride[2]};
@@ -1481,19 +1667,14 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
             CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3,
                                           cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    lumacu_frame_stats hs[64];
     if (stats)
-        CU_TRY(ctx, cudaMemcpyAsync(hs, d_stats, sizeof(lumacu_frame_stats) * nb, cudaMemcpyDeviceToHost, ctx->s_out));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
-    if (stats) {
-        *stats = hs[0];
-        for (int b = 1; b < nb; b++) {
-            stats->sum += hs[b].sum;
-            stats->max = fmaxf(stats->max, hs[b].max);
-            stats->min = fminf(stats->min, hs[b].min);
-        }
-    }
-    return LUMACU_OK;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_pin, d_stats, sizeof(lumacu_frame_stats) * nb, cudaMemcpyDeviceToHost, ctx->s_out));
+    if (write_back) /* with the in-place side effect the caller's frame is busy until the last D2H copy */
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_input, ctx->s_out));
+    ctx->pending = true;
+    ctx->pending_stats = stats;
+    ctx->pending_bands = nb;
+    return async ? LUMACU_OK : finish_pending(ctx);
 }
 
 extern "C" int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
@@ -1505,7 +1686,7 @@ try {
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
 static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
-                       int profile, float pre_scaling, float *rgb, bool passthrough)
+                       int profile, float pre_scaling, float *rgb, bool passthrough, bool async = false)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
@@ -1517,6 +1698,8 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
     if (rc)
         return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
+        return rc;
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
@@ -1548,6 +1731,8 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
             bp[p] = dp[p] + (size_t)py0 * dstride[p];
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        if (b == nb - 1)
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_input, ctx->s_in)); /* the caller's planes have been read completely */
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         float *band = d_rgb + (size_t)y0 * w;
         rc = decode_launch(ctx, bp, dstride, w, rows, profile, pre_scaling, band, 1, 0, nullptr, ctx->stream, opt);
@@ -1558,8 +1743,10 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
         CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3, cudaMemcpyDeviceToHost,
                                       ctx->s_out));
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
-    return LUMACU_OK;
+    ctx->pending = true;
+    ctx->pending_stats = nullptr;
+    ctx->pending_bands = nb;
+    return async ? LUMACU_OK : finish_pending(ctx);
 }
 
 extern "C" int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
@@ -1568,6 +1755,44 @@ try {
     return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, rgb, false);
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
+/* ---- asynchronous pair: queue the call, return; lumacu_wait_input / lumacu_wait complete it ------------------ */
+extern "C" int lumacu_encode_async(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
+                                   uint8_t *const planes[3], const int32_t strides[3], int write_back,
+                                   lumacu_frame_stats *stats)
+try {
+    return host_encode(ctx, rgb, w, h, profile, pre_scaling, planes, strides, write_back, stats, false, true);
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_decode_async(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                                   uint32_t h, int profile, float pre_scaling, float *rgb)
+try {
+    return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, rgb, false, true);
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_wait_input(lumacu_ctx *ctx)
+try {
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!ctx->pending)
+        return LUMACU_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev_input));
+    return LUMACU_OK;
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_wait(lumacu_ctx *ctx)
+try {
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    return finish_pending(ctx);
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_pending(const lumacu_ctx *ctx) { return (ctx && ctx->pending) ? 1 : 0; }
 
 extern "C" int lumacu_display(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
                               int profile, float pre_scaling, const lumacu_display_params *params, uint8_t *rgba,
@@ -1583,6 +1808,8 @@ try {
     if (rc)
         return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if ((rc = finish_pending(ctx)))
+        return rc;
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
     const int bytes = profile > 1 ? 2 : 1;
@@ -1641,8 +1868,8 @@ try {
     if (!bytes)
         return LUMACU_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    int rc = reserve(ctx, ctx->d_rgb, bytes);
-    if (rc)
+    int rc = finish_pending(ctx);
+    if (rc || (rc = reserve(ctx, ctx->d_rgb, bytes)))
         return rc;
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb.p, frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
     rc = lumacu_transform_color_space_dev(ctx, (float *)ctx->d_rgb.p, w, h, to_cs, sc, ctx->stream);
@@ -1665,8 +1892,8 @@ static int elementwise_host(lumacu_ctx *ctx, const float *in, float *out, size_t
     if (!in || !out)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "NULL pointer");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    int rc = reserve(ctx, ctx->d_aux, n * 8);
-    if (rc)
+    int rc = finish_pending(ctx);
+    if (rc || (rc = reserve(ctx, ctx->d_aux, n * 8)))
         return rc;
     float *d_in = (float *)ctx->d_aux.p, *d_out = d_in + n;
     CU_TRY(ctx, cudaMemcpyAsync(d_in, in, n * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -99,6 +99,7 @@ public:
     /* ---- additions ---- */
     void setStrictSideEffect(bool on) { m_strict = on; }
     void setDevice(int device) { m_quant.setDevice(device); } /* which GPU runs the transform (before initialize) */
+    LumaQuantizer *getQuantizer() { return &m_quant; } /* e.g. for LumaQuantizer::broadcast */
     vpx_image_t *getRawFrame() { return &m_rawFrame; } /* the planes the last encode() produced */
     double lastMeanLuminance() const { return m_lastMean; }
 

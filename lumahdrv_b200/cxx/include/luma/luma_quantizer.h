@@ -60,6 +60,10 @@ public:
      * before the first use; one object per GPU (on its own host thread) is how a process drives several GPUs. */
     void setDevice(int device);
     colorSpace_t colorSpace() const { return m_colorSpace; }
+    /* One process, several GPUs: q[root]'s quantizer (host table AND the device search tables derived from it) is
+     * copied to every other object, device to device (lumacu_broadcast_quantizer), instead of each object
+     * re-deriving its own.  Call after setQuantizer / LumaDecoder::initialize on the root. */
+    static void broadcast(LumaQuantizer *const q[], int n, int root);
 
 private:
     LumaQuantizer(const LumaQuantizer &);

@@ -127,6 +127,47 @@ void LumaQuantizer::setDevice(int device)
     m_device = device;
 }
 
+void LumaQuantizer::broadcast(LumaQuantizer *const q[], int n, int root)
+{
+    if (!q || n < 1 || root < 0 || root >= n || !q[root])
+        throw LumaException("LumaQuantizer::broadcast: bad arguments");
+    LumaQuantizer *src = q[root];
+    src->sync(); /* context exists, tables uploaded */
+    std::vector<lumacu_ctx *> ctxs((size_t)n, (lumacu_ctx *)NULL);
+    for (int i = 0; i < n; i++) {
+        if (!q[i])
+            throw LumaException("LumaQuantizer::broadcast: NULL object");
+        if (!q[i]->m_ctx) {
+            const int rc = lumacu_create(q[i]->m_device >= 0 ? q[i]->m_device : env_device(), &q[i]->m_ctx);
+            if (rc != LUMACU_OK) {
+                q[i]->m_ctx = NULL;
+                throw_status(NULL, rc, "LumaQuantizer: no usable CUDA device (this build has no CPU path)");
+            }
+        }
+        ctxs[(size_t)i] = q[i]->m_ctx;
+    }
+    const int rc = lumacu_broadcast_quantizer(&ctxs[0], n, root);
+    if (rc != LUMACU_OK)
+        throw_status(src->m_ctx, rc, "LumaQuantizer::broadcast");
+    for (int i = 0; i < n; i++) {
+        LumaQuantizer *d = q[i];
+        if (d == src)
+            continue;
+        d->m_colorSpace = src->m_colorSpace;
+        d->m_mapping = src->m_mapping;
+        d->m_Lmax = src->m_Lmax;
+        d->m_Lmin = src->m_Lmin;
+        d->m_maxVal = src->m_maxVal;
+        d->m_maxValColor = src->m_maxValColor;
+        d->m_bitdepth = src->m_bitdepth;
+        d->m_bitdepthColor = src->m_bitdepthColor;
+        d->m_uploaded = src->m_uploaded; /* what the device holds now: no re-derivation at the next use */
+        d->m_uploadedCs = src->m_uploadedCs;
+        d->m_uploadedMaxValColor = src->m_uploadedMaxValColor;
+        d->m_uploadedLmax = src->m_uploadedLmax;
+    }
+}
+
 lumacu_ctx *LumaQuantizer::device() const
 {
     sync();

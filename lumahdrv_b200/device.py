@@ -119,6 +119,31 @@ class DeviceTransform:
                                                       _stream_ptr(self.device)), hnd, "lumacu_half_rgba_to_frame_dev")
         return out
 
+    def pfs_xyz_to_frame(self, x: torch.Tensor, y: torch.Tensor, z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """PfsInterface::readFrame's colour step (src/pfs_interface.cpp:80-102): the X, Y, Z channel arrays of a PFS
+        frame ([h, w] f32 each) -> planar RGB frame [3, h, w]."""
+        for c in (x, y, z):
+            if c.dtype != torch.float32 or c.dim() != 2 or not c.is_contiguous() or not c.is_cuda or c.shape != x.shape:
+                raise LumaException("x, y, z must be contiguous CUDA float32 [h, w] tensors of one size", 1)
+        h, w = x.shape
+        if out is None:
+            out = torch.empty((3, h, w), dtype=torch.float32, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_pfs_xyz_to_frame_dev(hnd, x.data_ptr(), y.data_ptr(), z.data_ptr(), w, h, out.data_ptr(),
+                                                    _stream_ptr(self.device)), hnd, "lumacu_pfs_xyz_to_frame_dev")
+        return out
+
+    def frame_to_pfs_xyz(self, rgb: torch.Tensor):
+        """PfsInterface::writeFrame's colour step (src/pfs_interface.cpp:136-140): planar RGB frame -> X, Y, Z arrays."""
+        if rgb.dtype != torch.float32 or rgb.dim() != 3 or rgb.shape[0] != 3 or not rgb.is_contiguous() or not rgb.is_cuda:
+            raise LumaException("rgb must be a contiguous CUDA float32 [3, h, w] tensor", 1)
+        _, h, w = rgb.shape
+        xyz = torch.empty((3, h, w), dtype=torch.float32, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_frame_to_pfs_xyz_dev(hnd, rgb.data_ptr(), w, h, xyz[0].data_ptr(), xyz[1].data_ptr(),
+                                                    xyz[2].data_ptr(), _stream_ptr(self.device)), hnd, "lumacu_frame_to_pfs_xyz_dev")
+        return xyz[0], xyz[1], xyz[2]
+
     @property
     def launch_count(self) -> int:
         return self.quant.ctx.launch_count

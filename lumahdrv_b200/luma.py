@@ -433,8 +433,9 @@ class LumaDecoder:
         return self.m_frame
 
     def display(self, planes, w: int, h: int, exposure: float = 1.0, gamma: float = 2.2, user_scaling: float = 1.0,
-                do_tmo: bool = False, ldr_sim: bool = False, profile: int | None = None) -> np.ndarray:
-        """The player's display path (src/lumaplay_dequantizer.frag:70-157): planes -> 8-bit RGBA [h, w, 4]."""
+                do_tmo: bool = False, ldr_sim: bool = False, profile: int | None = None, linear: bool = False) -> np.ndarray:
+        """The player's display path (src/lumaplay_dequantizer.frag:70-157): planes -> 8-bit RGBA [h, w, 4].
+        linear=True samples like the player's GL_LINEAR textures (bilinear chroma, half-code LUT fetch)."""
         if not self.m_initialized:
             raise LumaException("LumaDecoder: not initialized", 3)
         profile = self.m_params.profile if profile is None else int(profile)
@@ -442,7 +443,7 @@ class LumaDecoder:
         q._upload()
         ptrs, strides = _plane_args(planes)
         out = np.empty((h, w, 4), dtype=np.uint8)
-        p = _lib.DisplayParams(float(exposure), float(gamma), float(user_scaling), int(do_tmo), int(ldr_sim))
+        p = _lib.DisplayParams(float(exposure), float(gamma), float(user_scaling), int(do_tmo), int(ldr_sim), int(linear))
         hnd = q.ctx.handle
         check(q._lib.lumacu_display(hnd, ptrs, strides, w, h, profile, float(self.m_params.preScaling), C.byref(p),
                                     out.ctypes.data, w * 4), hnd, "lumacu_display")

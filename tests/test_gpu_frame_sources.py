@@ -59,3 +59,30 @@ def test_half_rgba_rejects_luminance_only(dt, lumalib):
     import torch
     with pytest.raises(lumalib.LumaException, match="luminance only"):
         dt.half_rgba_to_frame(torch.zeros((4, 4, 4), dtype=torch.float16, device="cuda"), channels=16)
+
+
+def test_pfs_xyz_channels_to_frame_and_back(dt, po):
+    """PfsInterface::readFrame / writeFrame colour steps (src/pfs_interface.cpp:84, :140).  pfstools is not in the
+    reference tree (parity unpinned against libpfs); its D65 matrices are the constants of the reference's own
+    xyz2rgbMat / rgb2xyzMat, so XYZ -> RGB is pinned against the reference's own XYZ inverse transform with sc = 1
+    (src/luma_quantizer.cpp:378-395: same matrix, same association, no clamp) and RGB -> XYZ against a float32
+    restatement of m0*a + m1*b + m2*c."""
+    import torch
+    h, w = 270, 482
+    rng = np.random.default_rng(8)
+    xyz = np.power(np.float32(10.0), rng.uniform(-4, 5, size=(3, h, w)).astype(np.float32)).astype(np.float32)
+    xyz[:, 0, :6] = np.array([0.0, -1.5, np.inf, np.nan, 1e-42, 3e38], dtype=np.float32)
+    d = [torch.from_numpy(xyz[c].copy()).cuda() for c in range(3)]
+    got = dt.pfs_xyz_to_frame(*d).cpu().numpy()
+    ref = xyz.copy()
+    assert po.Oracle().setQuantizer("PQ", 11, "XYZ", 8).transformColorSpace(ref, False, 1.0)
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), nan) and np.array_equal(got.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])
+    # and back: RGB -> XYZ, unclamped
+    m = np.array([[0.412424, 0.357579, 0.180464], [0.212656, 0.715158, 0.072186], [0.019332, 0.119193, 0.950444]], dtype=np.float32)
+    rgb = np.abs(xyz)
+    with np.errstate(all="ignore"):
+        want = np.stack([(m[r, 0] * rgb[0] + m[r, 1] * rgb[1]) + m[r, 2] * rgb[2] for r in range(3)]).astype(np.float32)
+    back = torch.stack(dt.frame_to_pfs_xyz(torch.from_numpy(rgb).cuda())).cpu().numpy()
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(back), nan) and np.array_equal(back.view(np.uint32)[~nan], want.view(np.uint32)[~nan])

@@ -109,3 +109,72 @@ def test_host_register_roundtrip(lumalib):
     assert lib.lumacu_host_register(C.c_void_p(buf.ctypes.data), buf.nbytes) == 0
     assert lib.lumacu_host_register(C.c_void_p(buf.ctypes.data), buf.nbytes) == 0  # twice is fine
     assert lib.lumacu_host_unregister(C.c_void_p(buf.ctypes.data)) == 0
+
+
+def test_broadcast_quantizer_and_async_pair_through_the_c_abi(lumalib, po):
+    """lumacu_broadcast_quantizer: contexts that never saw lumacu_set_quantizer encode/decode with the root's tables
+    (an arbitrary LUT, so nothing could have been rebuilt locally).  lumacu_encode_async / lumacu_decode_async +
+    lumacu_wait_input / lumacu_wait give the same bytes as the blocking calls, and a second call on a busy context
+    first completes the one in flight."""
+    import ctypes as C
+
+    import torch
+    L = lumalib
+    lib = L.lib()
+    n_dev = torch.cuda.device_count()
+    ctxs = [L.Context(i % n_dev) for i in range(3)]
+    rng = np.random.default_rng(5)
+    lut = np.sort(np.unique(np.power(10.0, rng.uniform(-3, 4, 4096)).astype(np.float32)))[:1024].copy()
+    h0 = ctxs[0].handle
+    L._lib.check(lib.lumacu_set_quantizer(h0, lut.ctypes.data, lut.size, 255, L.CS_LUV, 1e4), h0, "set")
+    arr = (C.c_void_p * 3)(*[c.handle for c in ctxs])
+    assert lib.lumacu_broadcast_quantizer(arr, 3, 0) == 0
+    assert lib.lumacu_broadcast_quantizer(arr, 3, 5) == 1 and lib.lumacu_broadcast_quantizer(None, 3, 0) == 1
+    # the receivers hold the root's host-side copy too
+    got = np.zeros(1024, np.float32)
+    n, mvc, cs, lm = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_float()
+    assert lib.lumacu_get_quantizer(ctxs[2].handle, got.ctypes.data, got.size, C.byref(n), C.byref(mvc), C.byref(cs), C.byref(lm)) == 0
+    assert n.value == 1024 and mvc.value == 255 and cs.value == L.CS_LUV and lm.value == 1e4 and np.array_equal(got, lut)
+
+    o = po.Oracle().setQuantizer("LINEAR", 10, "LUV", 8)
+    o.setMapping(lut)
+    w, h = 512, 128
+    frames = [po.noise_frame(w, h, seed=40 + i) for i in range(3)]
+    refs = [o.encode(f.copy(), 2, 1.0)[0] for f in frames]
+    strides = L.vpx_strides(w, 2)
+    pinned = []
+
+    def pin(shape, dtype):
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        pinned.append(t)
+        return t.numpy()
+
+    ins = [pin((3, h, w), torch.float32) for _ in range(3)]
+    outs = [pin((3, h, w), torch.float32) for _ in range(3)]
+    planes = [[pin((ph, st), torch.uint8) for (pw, ph), st in zip(L.plane_dims(w, h, 2), strides)] for _ in range(3)]
+    stats = [L._lib.FrameStats() for _ in range(3)]
+    for i, c in enumerate(ctxs):  # queue on every context first, collect afterwards
+        ins[i][...] = frames[i]
+        ptrs, st = L.luma._plane_args(planes[i])
+        assert lib.lumacu_encode_async(c.handle, ins[i].ctypes.data, w, h, 2, 1.0, ptrs, st, 0, C.byref(stats[i])) == 0
+        assert lib.lumacu_pending(c.handle) == 1
+    for i, c in enumerate(ctxs):
+        assert lib.lumacu_wait_input(c.handle) == 0
+        ins[i][...] = -1.0  # the input may be reused now
+        assert lib.lumacu_wait(c.handle) == 0 and lib.lumacu_pending(c.handle) == 0
+        for a, b, (pw, ph) in zip(planes[i], refs[i], L.plane_dims(w, h, 2)):
+            assert np.array_equal(a[:ph, :pw * 2], b[:ph, :pw * 2]), f"context {i}"
+        fc = frames[i].copy()
+        o.transformColorSpace(fc, True, 1.0)
+        assert stats[i].max == float(fc[0].max()) and stats[i].sum == pytest.approx(float(fc[0].astype(np.float64).sum()), rel=1e-6)
+    for i, c in enumerate(ctxs):
+        ptrs, st = L.luma._plane_args(planes[i])
+        assert lib.lumacu_decode_async(c.handle, ptrs, st, w, h, 2, 1.0, outs[i].ctypes.data) == 0
+    # a blocking call on a busy context completes the pending one first (context 0: decode again, blocking)
+    ptrs, st = L.luma._plane_args(planes[0])
+    assert lib.lumacu_decode(ctxs[0].handle, ptrs, st, w, h, 2, 1.0, outs[0].ctypes.data) == 0
+    for i, c in enumerate(ctxs):
+        assert lib.lumacu_wait(c.handle) == 0
+        assert bits_equal(outs[i], o.decode(refs[i], w, h, 2, 1.0)), f"context {i}"
+    for c in ctxs:
+        c.close()

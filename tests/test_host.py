@@ -20,7 +20,7 @@ def test_abi_exports_every_declared_symbol(lumalib):
     handle = lumalib.lib()
     for name in declared:
         assert hasattr(handle, name), name
-    assert handle.lumacu_version() == 100
+    assert handle.lumacu_version() == 200
     assert handle.lumacu_status_name(6) == b"LUMACU_ERR_NO_DEVICE"
 
 
