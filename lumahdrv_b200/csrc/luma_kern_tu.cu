@@ -121,42 +121,49 @@ void launch_display_linear(unsigned blocks, unsigned n_frames, cudaStream_t st, 
  * Every configuration exists as variant 4 (PF 0, the default); the headline instantiation (Lu'v', 4:2:0,
  * 16-bit planes, walk 1) is additionally compiled in more variants so that scripts/sweep.py can re-measure
  * the choice. */
-template <bool SUB, int BYTES, int PF, bool PRESC>
+template <bool SUB, int BYTES, int PF, bool PRESC, bool FASTC>
 static enc_fn pick_walk(int walk)
 {
 #if LUMA_TU_CS == 0 || LUMA_TU_CS == 3
     if (walk == 0) /* direct search table over [1e-4, 1e8] (positive searched values: Lu'v' Y, XYZ) */
-        return encode_fast_kernel<kCS, SUB, BYTES, 0, PF, 4, PRESC>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 0, PF, 4, PRESC, FASTC>;
 #else
     if (walk == 0)
         return nullptr;
 #endif
     if (walk == -1) /* direct search table over the thresholds' own range (both clamps on the device) */
-        return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4, PRESC>;
+        return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4, PRESC, FASTC>;
 #if LUMA_TU_CS == 0
     /* the headline colour space gets the exact walk length */
     if (walk <= 1)
-        return encode_fast_kernel<kCS, SUB, BYTES, 1, PF, 4, PRESC>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 1, PF, 4, PRESC, FASTC>;
     if (walk == 2)
-        return encode_fast_kernel<kCS, SUB, BYTES, 2, PF, 4, PRESC>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 2, PF, 4, PRESC, FASTC>;
 #endif
     if (walk <= 4)
-        return encode_fast_kernel<kCS, SUB, BYTES, 4, PF, 4, PRESC>;
+        return encode_fast_kernel<kCS, SUB, BYTES, 4, PF, 4, PRESC, FASTC>;
     return nullptr;
 }
 
 template <int PF, bool PRESC>
-static enc_fn pick_enc_cfg(bool sub, int bytes, int walk)
+static enc_fn pick_enc_cfg(bool sub, int bytes, int walk, bool screened)
 {
+#if LUMA_TU_CS == 0
+    if (sub && screened) /* Lu'v' 4:2:0 with screened chroma (luma_fast.cuh FASTC) */
+        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, true>(walk) : pick_walk<true, 1, PF, PRESC, true>(walk);
+#endif
+    (void)screened;
     if (sub)
-        return bytes == 2 ? pick_walk<true, 2, PF, PRESC>(walk) : pick_walk<true, 1, PF, PRESC>(walk);
-    return bytes == 2 ? pick_walk<false, 2, PF, PRESC>(walk) : pick_walk<false, 1, PF, PRESC>(walk);
+        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, false>(walk) : pick_walk<true, 1, PF, PRESC, false>(walk);
+    return bytes == 2 ? pick_walk<false, 2, PF, PRESC, false>(walk) : pick_walk<false, 1, PF, PRESC, false>(walk);
 }
 
 enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk, int variant, bool prescale)
 {
-    if (variant == 4)
-        return prescale ? pick_enc_cfg<0, true>(sub, bytes, walk) : pick_enc_cfg<0, false>(sub, bytes, walk);
+    if (variant == 4 || variant == kEncVariantScreened) {
+        const bool scr = variant == kEncVariantScreened;
+        return prescale ? pick_enc_cfg<0, true>(sub, bytes, walk, scr) : pick_enc_cfg<0, false>(sub, bytes, walk, scr);
+    }
     if (prescale)
         return nullptr; /* the tuning variants exist for preScaling == 1 only */
 #if LUMA_TU_CS == 0

@@ -71,6 +71,9 @@ struct EncArgs {
     FrameStatsDev *stats;  /* [frames] */
     float2 nz;             /* (-0.0f, -0.0f), see luma_fast.cuh mul2_nc */
     int passthrough;       /* generic kernels: the frame is already colour-transformed (setChannels) */
+    /* screened-chroma kernels (luma_fast.cuh FASTC): t = screen_k * (sum of the 2x2 block's X/D resp. Y/D) + 0.5 with
+     * screen_k1 = RN(maxC/4 * 4 * 410/255), screen_k2 = RN(maxC/4 * 9 * 410/255) */
+    float screen_k1, screen_k2;
     /* tensor-map staged kernels: CUtensorMap over the frame batch, dims {w, h, 3 planes, frames} of f32,
      * box {128, 2, 3, 1} (opaque 128 bytes so that this header does not need cuda.h) */
     alignas(64) unsigned char rgb_tmap[128];

@@ -127,7 +127,7 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
     cpu_planes, _ = o.encode(rgb[0].cpu().numpy().copy(), 2, 1.0)
     for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
         assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
-    for enc_v, dec_v, cap in [(3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
+    for enc_v, dec_v, cap in [(4, 0, 0), (6, 0, 0), (1006, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
                               (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
         ctx.set_tuning(enc_v, dec_v, cap)
         planes = t.encode(rgb)
@@ -136,6 +136,92 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
         out = t.decode(ref_planes, w, h)
         assert torch.equal(out.view(torch.int32), ref_out.view(torch.int32)), f"decode variant {dec_v} cap {cap}"
     ctx.set_tuning(0, 0, 0)
+
+
+def _boundary_frame(w, h, seed, max_c=255.0, rel_span=2e-5):
+    """2x2-constant blocks whose chroma code sits within +-rel_span (relative) of a rounding boundary: for every block
+    pick R, B at random and solve (float64 bisection on G) 410/255 * maxC * u'(R,G,B) + 0.5 = n (1 + d), d uniform in
+    +-rel_span, u' = 4X / (X + 15Y + 3Z); half of the blocks do the same for v' = 9Y / (X + 15Y + 3Z)."""
+    rng = np.random.default_rng(seed)
+    bh, bw = h // 2, w // 2
+    m = np.array([[0.412424, 0.357579, 0.180464], [0.212656, 0.715158, 0.072186], [0.019332, 0.119193, 0.950444]])
+    R = np.power(10.0, rng.uniform(-2, 4, (bh, bw)))
+    B = np.power(10.0, rng.uniform(-2, 4, (bh, bw)))
+    use_v = rng.random((bh, bw)) < 0.5
+
+    def t_of(G):
+        X = m[0, 0] * R + m[0, 1] * G + m[0, 2] * B
+        Y = m[1, 0] * R + m[1, 1] * G + m[1, 2] * B
+        Z = m[2, 0] * R + m[2, 1] * G + m[2, 2] * B
+        D = X + 15 * Y + 3 * Z
+        return max_c * (410.0 / 255.0) * np.where(use_v, 9 * Y, 4 * X) / D + 0.5
+
+    lo, hi = np.full((bh, bw), 1e-3), np.full((bh, bw), 1e5)
+    t_lo, t_hi = t_of(lo), t_of(hi)
+    a, b = np.minimum(t_lo, t_hi), np.maximum(t_lo, t_hi)
+    n = np.floor(a + rng.random((bh, bw)) * (b - a))
+    n = np.clip(n, np.ceil(a) + 0, np.floor(b) - 0)
+    target = n * (1.0 + rng.uniform(-rel_span, rel_span, (bh, bw)))
+    inc = t_hi > t_lo
+    for _ in range(80):
+        mid = np.sqrt(lo * hi)
+        below = (t_of(mid) < target) == inc
+        lo = np.where(below, mid, lo)
+        hi = np.where(below, hi, mid)
+    G = np.sqrt(lo * hi)
+    blocks = np.stack([R, G, B]).astype(np.float32)
+    return np.ascontiguousarray(np.repeat(np.repeat(blocks, 2, axis=1), 2, axis=2))
+
+
+@pytest.mark.parametrize("cbits,sc", [(8, 1.0), (10, 1.0), (8, 3.5)])
+def test_screened_chroma_equals_exact_chain(lumalib, po, torch_cuda, cbits, sc):
+    """The screened-chroma encode kernel (Lu'v' 4:2:0 default; luma_fast.cuh FASTC) against the exact-chain tuned kernel
+    (variant 4, itself pinned against the oracle everywhere else) on 100+ Mpixel of content chosen to stress the screen:
+    chroma values straddling the code boundaries by relative distances around the acceptance threshold (2^-18),
+    near-grey, saturated primaries, very dark, huge / negative / NaN / infinite samples, plus plain noise -- and a
+    whole-frame check of one boundary frame against the CPU oracle."""
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+
+    w, h = 1920, 1080
+    t = DeviceTransform(0, colorBitDepth=cbits, preScaling=sc)
+    ctx = t.quant.ctx
+    max_c = float((1 << cbits) - 1)
+    rng = np.random.default_rng(99)
+    frames = [_boundary_frame(w, h, 1, max_c, 2e-5), _boundary_frame(w, h, 2, max_c, 6e-6), _boundary_frame(w, h, 3, max_c, 2e-7)]
+    grey = po.noise_frame(w, h, seed=5)
+    grey[1] = grey[0] * (1 + rng.uniform(-1e-3, 1e-3, (h, w)).astype(np.float32))
+    grey[2] = grey[0] * (1 + rng.uniform(-1e-3, 1e-3, (h, w)).astype(np.float32))
+    frames.append(grey)
+    prim = po.noise_frame(w, h, seed=6)
+    prim[rng.integers(0, 3, (h, w))[None].repeat(3, 0) == np.arange(3)[:, None, None]] *= np.float32(1e-6)  # one channel ~ 0
+    frames.append(prim)
+    frames.append(po.noise_frame(w, h, seed=7) * np.float32(1e-5))                     # everything below the 1e-4 clamp
+    frames.append((po.noise_frame(w, h, seed=8) * np.float32(3e4)).astype(np.float32))  # up to 3e8: above 9e7 and the 1e8 clamp
+    wild = po.noise_frame(w, h, seed=9)
+    k = rng.integers(0, wild.size, 20000)
+    wild.reshape(-1)[k] = rng.choice(np.array([-1.0, -1e-3, 0.0, np.nan, np.inf, -np.inf, 9.0e7, 9.1e7, 1e-45, 3e38], np.float32), k.size)
+    frames.append(wild)
+    frames += [po.noise_frame(w, h, seed=20 + i) for i in range(4)]
+    frames = [np.ascontiguousarray(f / np.float32(sc)) if sc != 1.0 else f for f in frames]
+    rgb = torch.from_numpy(np.stack(frames)).cuda()
+    ctx.set_tuning(4)
+    exact = [p.clone() for p in t.encode(rgb)]
+    assert ctx.last_kernel_path == 1
+    for tune in (0, 6, 1006):  # default (= screened), screened explicitly, screened + bucket/threshold luma search
+        ctx.set_tuning(tune)
+        got = t.encode(rgb)
+        assert ctx.last_kernel_path == 1
+        for p, (a, b) in enumerate(zip(got, exact)):
+            if not torch.equal(a, b):
+                bad = (a != b).nonzero()
+                raise AssertionError(f"tuning {tune}: plane {p} differs in {bad.shape[0]} bytes, first at {bad[0].tolist()}")
+    ctx.set_tuning(0)
+    o = po.Oracle().setQuantizer("PQ", 11, "LUV", cbits)
+    for f in (1, 7):
+        cpu_planes, _ = o.encode(frames[f].copy(), 2, sc)
+        for a, b, (pw, ph) in zip(exact, cpu_planes, po.plane_dims(w, h, 2)):
+            assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
 
 
 def test_plain_c_example_round_trips(torch_cuda):

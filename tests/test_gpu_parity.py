@@ -61,9 +61,10 @@ def check_frame(L, po, frame, enc, o, profile, sc, cs, strides=None):
     # reference's in-place side effect, then once more with it (always the generic kernel)
     # path 0 = tuned kernel with its default luma search (direct table where the LUT qualifies), 2 = tuned kernel
     # forced onto the bucket + threshold search, 1 = generic kernel
-    for path in (0, 2, 1):
+    # 3 = tuned kernel with the exact chroma chain (the default for Lu'v' 4:2:0 screens chroma first, luma_fast.cuh FASTC)
+    for path in (0, 2, 3, 1):
         enc.m_quant.ctx.set_kernel_path(1 if path == 1 else 0)
-        enc.m_quant.ctx.set_tuning(1000 if path == 2 else 0)
+        enc.m_quant.ctx.set_tuning({2: 1000, 3: 4}.get(path, 0))
         enc.strict_side_effect = False
         f_in = frame.copy()
         planes_path = L.alloc_planes(w, h, profile, strides, fill=0xAB)
