@@ -335,6 +335,10 @@ int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, ui
  * the generic kernels (a literal transcription of the reference loops; used by the tests to
  * cross-check the two).  Both produce identical bits. */
 int lumacu_set_kernel_path(lumacu_ctx *ctx, int path);
+/* CS_YCBCR: the tuned kernels read two of the per-pixel PQ powers from exhaustive device-built tables (45 MB per
+ * context, L2-resident; DESIGN.md "YCbCr").  enable = 0 makes them evaluate every powf per pixel instead (tests and
+ * sweeps; same bits either way).  Default: enabled. */
+int lumacu_set_pq_tables(lumacu_ctx *ctx, int enable);
 /* 1 if the last encode/decode launch on this context ran a tuned kernel, 0 if generic. */
 int lumacu_last_kernel_path(const lumacu_ctx *ctx);
 /* Host-pointer entry points cut a frame into row bands whose H2D copy, kernel and D2H copy overlap on three

@@ -120,6 +120,7 @@ SIGNATURES = {
     "lumacu_quantize_dev": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint, _P]),
     "lumacu_dequantize_dev": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_uint, _P]),
     "lumacu_set_kernel_path": (C.c_int, [_P, C.c_int]),
+    "lumacu_set_pq_tables": (C.c_int, [_P, C.c_int]),
     "lumacu_last_kernel_path": (C.c_int, [_P]),
     "lumacu_launch_count": (C.c_uint64, [_P]),
     "lumacu_search_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),

@@ -48,6 +48,10 @@ void launch_quantize(unsigned blocks, size_t smem, cudaStream_t st, const QuantD
 void launch_dequantize(unsigned blocks, cudaStream_t st, const QuantDev &q, const float *in, float *out, size_t n,
                        int use_lut);
 const void *quantize_kernel_ptr();
+/* CS_YCBCR PQ tables (luma_pq_tables.cuh): pqd = kPqTabPqdBytes, pqe = kPqTabPqeBytes of device memory */
+constexpr size_t kPqTabPqdBytes = (size_t)((0x3F800000u - 0x3B800000u + 1u + 31u) / 32u) * 16u;
+constexpr size_t kPqTabPqeBytes = (size_t)(0x3F8147AEu - 0x3F55C28Fu + 1u) * 4u;
+void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *pqe, float l_max);
 void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
 void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);
 void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,

@@ -19,6 +19,10 @@
 #include "luma_fast.cuh"
 #else
 #include "luma_kernels.cuh"
+#if LUMA_TU_CS == 2
+#define LUMA_PQ_TABLE_BUILDERS 1
+#include "luma_pq_tables.cuh"
+#endif
 #endif
 
 #define LUMA_CAT2(a, b) a##b
@@ -53,6 +57,15 @@ dec_fn LUMA_CAT(get_decode_generic_cs, LUMA_TU_CS)(bool sub, int bytes, bool vec
         return vec ? decode_kernel<kCS, false, 2, true> : decode_kernel<kCS, false, 2, false>;
     return vec ? decode_kernel<kCS, false, 1, true> : decode_kernel<kCS, false, 1, false>;
 }
+
+#if LUMA_TU_CS == 2
+/* builders of the CS_YCBCR PQ tables (luma_pq_tables.cuh) live in this unit */
+void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *pqe, float l_max)
+{
+    build_pqd_kernel<<<blocks, 256, 0, st>>>((uint4 *)pqd, l_max);
+    build_pqe_kernel<<<blocks, 256, 0, st>>>(pqe);
+}
+#endif
 
 #if LUMA_TU_CS == 1
 /* the element-wise API kernels live in one unit only */

@@ -37,6 +37,10 @@ struct QuantDev {
     /* CS_YCBCR decode: code -> ((255 PQenc(lut[code])) - 16) / 219 (src/luma_quantizer.cpp:447-448), host-built with the
      * host libm: two of the eight per-pixel powf calls become a table read.  NULL for the other colour spaces. */
     const float *ylut;
+    /* CS_YCBCR, tuned kernels: exhaustive L2-resident tables of PQ decode (step table over every float in [2^-8, 1]) and
+     * of the outer power of PQ encode (one entry per float in [0.835, 1.01]); luma_pq_tables.cuh.  NULL = evaluate. */
+    const uint4 *pqd;
+    const float *pqe;
 };
 
 constexpr int kThreads = 256;

@@ -1,0 +1,144 @@
+/*
+ * luma_pq_tables.cuh -- exhaustive, L2-resident tables of the two PQ curves for CS_YCBCR.
+ *
+ * CS_YCBCR evaluates PQ per pixel through libm powf (reference src/luma_quantizer.cpp:331-337,447-459,485-501): eight
+ * calls per pixel each way.  powf_glibc.cuh reproduces the host libm bit for bit, but one call is ~110 instructions
+ * (27 of them unfused FP64).  Two of the call sites have a SMALL domain once you look at what feeds them, so their
+ * results can be tabulated for EVERY possible input, with the exact device powf, once per quantizer:
+ *
+ *  (1) PQ decode, L * powf(max(0, Vp - c1) / (c2 - c3 Vp), 1/n) with Vp = powf(v, 1/m), is only ever applied to
+ *      v = clamp01(.) (inverse transform, :453-459) or to v = (219 y' + 16)/255 (forward, :340).  The exponent 1/m =
+ *      0.0127 makes Vp a staircase: ~40-79 consecutive floats v share one Vp, hence one result.  For every float v in
+ *      [2^-8, 1] the table holds, per bucket of 32 consecutive floats, the result below the step, the result above it
+ *      and the position of the step (pqd: 2.1 M buckets x 16 B = 33.5 MB).  The builder evaluates Vp for ALL 2^26 floats
+ *      of the range and marks a bucket irregular (lookup falls back to the exact evaluation) unless its 32 values are
+ *      "one value, then a second one" -- so glibc's rare non-monotonic roundings at a step edge cannot be misrepresented.
+ *  (2) the outer power of PQ encode, powf(b, m) with b = (c1 + c2 Lp) / (1 + c3 Lp): whatever Lp is, b lies in
+ *      [c1, c2/c3] = [0.8359, 1.00878] -- 2.85 M floats.  pqe holds powf(b, m) for each of them (11.4 MB).
+ *
+ * Both tables fit in the 126 MB L2 many times over; a lookup is one 32-byte sector from L2 (or L1, for neighbouring
+ * pixels of natural images) instead of 110-220 instructions.  The inner power of PQ encode, Lp = powf(x / Lmax, n),
+ * has an unbounded domain and stays an exact evaluation.  Every table entry is produced by powf_glibc itself, so a
+ * table lookup returns exactly what the per-pixel evaluation returns -- tests run both (tuned kernels: tables;
+ * generic kernels: per-pixel powf) against the oracle.
+ */
+#pragma once
+
+#include "luma_device.cuh"
+
+namespace lumacu {
+
+constexpr uint32_t kPqdKey0 = 0x3B800000u;                /* 2^-8 */
+constexpr uint32_t kPqdKeys = 0x3F800000u - kPqdKey0 + 1u; /* ... 1.0f inclusive */
+constexpr uint32_t kPqdBuckets = (kPqdKeys + 31u) / 32u;
+constexpr uint32_t kPqeKey0 = 0x3F55C28Fu;                /* 0.835f */
+constexpr uint32_t kPqeKeys = 0x3F8147AEu - kPqeKey0 + 1u; /* ... 1.01f inclusive */
+
+/* the tail of transformPQ(decode) once Vp is known (src/luma_quantizer.cpp:498-499) */
+__device__ __forceinline__ float pq_decode_from_vp(float Vp, float l_max)
+{
+    const float n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
+    const float inv_n = 1.0f / n;
+    const float num = fmaxf(0.0f, __fsub_rn(Vp, c1));
+    const float den = __fsub_rn(c2, __fmul_rn(c3, Vp));
+    return __fmul_rn(l_max, powf_glibc(__fdiv_rn(num, den), inv_n));
+}
+
+#ifdef LUMA_PQ_TABLE_BUILDERS /* one translation unit only (luma_kern_tu.cu, generic CS 2) */
+/* one warp per bucket of 32 consecutive floats */
+__global__ void __launch_bounds__(256) build_pqd_kernel(uint4 *tab, float l_max)
+{
+    powf_tables_stage();
+    const float m = 78.8438f;
+    const float inv_m = 1.0f / m;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < kPqdBuckets; b += warps) {
+        const float v = __uint_as_float(kPqdKey0 + b * 32u + lane);
+        const float Vp = powf_glibc(v, inv_m);
+        const uint32_t vb = __float_as_uint(Vp);
+        const uint32_t first = __shfl_sync(0xffffffffu, vb, 0), last = __shfl_sync(0xffffffffu, vb, 31);
+        const uint32_t m_lo = __ballot_sync(0xffffffffu, vb == first), m_hi = __ballot_sync(0xffffffffu, vb == last);
+        const uint32_t n_lo = __popc(m_lo);
+        /* regular: all equal, or a run of `first` followed by a run of `last` and nothing else */
+        const bool regular = (first == last) ? (m_lo == 0xffffffffu)
+                                             : ((m_lo | m_hi) == 0xffffffffu && m_lo == (0xffffffffu >> (32u - n_lo)));
+        float val = 0.0f;
+        if (lane == 0 || lane == 31)
+            val = pq_decode_from_vp(Vp, l_max);
+        const uint32_t v_lo = __shfl_sync(0xffffffffu, __float_as_uint(val), 0);
+        const uint32_t v_hi = __shfl_sync(0xffffffffu, __float_as_uint(val), 31);
+        if (lane == 0)
+            tab[b] = make_uint4(v_lo, v_hi, regular ? n_lo : 0xffffffffu, 0u);
+    }
+}
+
+__global__ void __launch_bounds__(256) build_pqe_kernel(float *tab)
+{
+    powf_tables_stage();
+    const float m = 78.8438f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < kPqeKeys; i += gridDim.x * blockDim.x)
+        tab[i] = powf_glibc(__uint_as_float(kPqeKey0 + i), m);
+}
+#endif /* LUMA_PQ_TABLE_BUILDERS */
+
+/* ---- lookups (tuned kernels) ---------------------------------------------------------------------------- */
+/* transformPQ(v, decode); identical to pq_decode(v, l_max) for every v */
+__device__ __forceinline__ float pq_decode_tab(const QuantDev &q, float v, float l_max)
+{
+    const uint32_t idx = __float_as_uint(v) - kPqdKey0;
+    if (q.pqd && idx < kPqdKeys) {
+        const uint4 e = __ldg(q.pqd + (idx >> 5));
+        if (e.z <= 32u)
+            return __uint_as_float((idx & 31u) < e.z ? e.x : e.y);
+    }
+    if (v == 0.0f) /* black and super-black (the [0,1] clamp): powf(0, .) = 0 all the way through */
+        return __fmul_rn(l_max, 0.0f);
+    return pq_decode(v, l_max); /* below 2^-8, NaN, or an irregular bucket: the exact evaluation */
+}
+
+/* transformPQ(val, encode); identical to pq_encode(val, l_max) for every val */
+__device__ __forceinline__ float pq_encode_tab(const QuantDev &q, float val, float l_max)
+{
+    const float m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
+    const float Lp = powf_glibc(__fdiv_rn(val, l_max), n);
+    const float num = __fadd_rn(c1, __fmul_rn(c2, Lp));
+    const float den = __fadd_rn(1.0f, __fmul_rn(c3, Lp));
+    const float b = __fdiv_rn(num, den);
+    const uint32_t idx = __float_as_uint(b) - kPqeKey0;
+    if (q.pqe && idx < kPqeKeys)
+        return __ldg(q.pqe + idx);
+    return powf_glibc(b, m);
+}
+
+/* BT.2020 Y'CbCr forward / inverse of one pixel with the tables (same expressions as ycbcr_forward_px /
+ * ycbcr_inverse_px in luma_device.cuh) */
+static __device__ __noinline__ float3 ycbcr_forward_px_tab(const QuantDev &q, float R, float G, float B, float l_max)
+{
+    const float Rp = pq_encode_tab(q, max_nan(R, 1e-10f), l_max);
+    const float Gp = pq_encode_tab(q, max_nan(G, 1e-10f), l_max);
+    const float Bp = pq_encode_tab(q, max_nan(B, 1e-10f), l_max);
+    const float y = dot3(0.2627f, 0.6780f, 0.0593f, Rp, Gp, Bp);
+    float3 c;
+    c.x = pq_decode_tab(q, __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y), 16.0f), 255.0f), l_max);
+    c.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp, y), 1.8814f)), 128.0f), 255.0f);
+    c.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp, y), 1.4746f)), 128.0f), 255.0f);
+    return c;
+}
+
+static __device__ __noinline__ float3 ycbcr_inverse_px_tab(const QuantDev &q, float y, float ca, float cb, float l_max)
+{
+    float blue = __fadd_rn(y, ca);
+    float red = __fadd_rn(y, cb);
+    float green = __fdiv_rn(__fsub_rn(__fsub_rn(y, __fmul_rn(0.2627f, red)), __fmul_rn(0.0593f, blue)), 0.6780f);
+    red = clamp01_std(red);
+    green = clamp01_std(green);
+    blue = clamp01_std(blue);
+    float3 o;
+    o.x = pq_decode_tab(q, red, l_max);
+    o.y = pq_decode_tab(q, green, l_max);
+    o.z = pq_decode_tab(q, blue, l_max);
+    return o;
+}
+
+} // namespace lumacu

@@ -103,6 +103,9 @@ struct lumacu_ctx {
     QuantDev q{};
     std::vector<float> h_lut;
     DeviceBuffer d_tables; /* lut | thr | bucket | ctab | dtab | ylut */
+    DeviceBuffer d_pq;       /* CS_YCBCR: pqd | pqe (luma_pq_tables.cuh), built on the device for pq_lmax */
+    float pq_lmax = 0.0f;
+    bool pq_valid = false, pq_off = false; /* pq_off: tests / sweeps run the tuned kernels without the tables */
     size_t tables_bytes = 0; /* bytes of d_tables in use (what lumacu_broadcast_quantizer copies to the peers) */
     float max_lum = 0.0f;
     size_t smem_enc = 0, smem_dec = 0;
@@ -525,7 +528,7 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_out)
         cudaStreamSynchronize(ctx->s_out); /* an asynchronous call the caller never waited for */
-    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
+    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
                             &ctx->d_aux})
         if (b->p)
             cudaFree(b->p);
@@ -767,6 +770,22 @@ try {
     if (!ylut.empty())
         CU_TRY(ctx, cudaMemcpy(d + off_ylut, ylut.data(), ylut.size() * 4, cudaMemcpyHostToDevice));
 
+    /* CS_YCBCR: exhaustive PQ tables for the tuned kernels, (re)built on the device when Lmax changes (~1 ms) */
+    if (color_space == CS_YCBCR && (!ctx->pq_valid || memcmp(&ctx->pq_lmax, &max_lum, sizeof(float)) != 0)) {
+        ctx->pq_valid = false;
+        if (reserve(ctx, ctx->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) == LUMACU_OK) {
+            launch_build_pq_tables((unsigned)ctx->sm_count * 8u, ctx->stream, ctx->d_pq.p,
+                                   (float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes), max_lum);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->launches += 2;
+            ctx->pq_lmax = max_lum;
+            ctx->pq_valid = true;
+        } else {
+            ctx->err.clear(); /* no room for the tables: the kernels evaluate PQ per pixel instead */
+        }
+    }
+
     QuantDev q{};
     q.lut = (const float *)d;
     q.thr = (const uint32_t *)(d + off_thr);
@@ -779,6 +798,10 @@ try {
     q.d_lo_key = d_lo_key;
     q.d_hi_key = d_hi_key;
     q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
+    if (color_space == CS_YCBCR && ctx->pq_valid) {
+        q.pqd = (const uint4 *)ctx->d_pq.p;
+        q.pqe = (const float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes);
+    }
     q.max_val = max_val;
     q.max_val_color = max_val_color;
     q.max_val_f = (float)max_val;
@@ -867,6 +890,25 @@ try {
         q.ctab = (const float *)rebase(q.ctab);
         q.dtab = (const uint32_t *)rebase(q.dtab);
         q.ylut = (const float *)rebase(q.ylut);
+        q.pqd = nullptr, q.pqe = nullptr;
+        if (src->color_space == CS_YCBCR && src->pq_valid) { /* built on the spot by the same deterministic kernels */
+            if (!dst->pq_valid || memcmp(&dst->pq_lmax, &src->pq_lmax, sizeof(float)) != 0) {
+                dst->pq_valid = false;
+                if (reserve(dst, dst->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) == LUMACU_OK) {
+                    launch_build_pq_tables((unsigned)dst->sm_count * 8u, dst->stream, dst->d_pq.p,
+                                           (float *)((unsigned char *)dst->d_pq.p + kPqTabPqdBytes), src->pq_lmax);
+                    CU_TRY(dst, cudaGetLastError());
+                    CU_TRY(dst, cudaStreamSynchronize(dst->stream));
+                    dst->launches += 2;
+                    dst->pq_lmax = src->pq_lmax;
+                    dst->pq_valid = true;
+                }
+            }
+            if (dst->pq_valid) {
+                q.pqd = (const uint4 *)dst->d_pq.p;
+                q.pqe = (const float *)((unsigned char *)dst->d_pq.p + kPqTabPqdBytes);
+            }
+        }
         dst->q = q;
         dst->tables_bytes = src->tables_bytes;
         dst->max_lum = src->max_lum;
@@ -929,6 +971,14 @@ try {
     return LUMACU_OK;
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
+extern "C" int lumacu_set_pq_tables(lumacu_ctx *ctx, int enable)
+{
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    ctx->pq_off = !enable;
+    return LUMACU_OK;
+}
 
 extern "C" int lumacu_last_kernel_path(const lumacu_ctx *ctx) { return (ctx && ctx->last_fast) ? 1 : 0; }
 
@@ -1127,6 +1177,8 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
 
     EncArgs a{};
     a.q = ctx->q;
+    if (ctx->pq_off)
+        a.q.pqd = nullptr, a.q.pqe = nullptr;
     a.rgb = d_rgb;
     a.rgb_out = d_rgb_out;
     a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
@@ -1252,6 +1304,8 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
 
     DecArgs a{};
     a.q = ctx->q;
+    if (ctx->pq_off)
+        a.q.pqd = nullptr, a.q.pqe = nullptr;
     a.rgb = d_rgb;
     a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;

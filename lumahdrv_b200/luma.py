@@ -108,6 +108,10 @@ class Context:
         check(self._lib.lumacu_set_tuning(self.handle, int(enc_variant), int(dec_variant), int(blocks_per_sm_cap)),
               self.handle, "lumacu_set_tuning")
 
+    def set_pq_tables(self, enable: bool) -> None:
+        """CS_YCBCR: tuned kernels with (default) or without the exhaustive PQ tables; identical bits."""
+        check(self._lib.lumacu_set_pq_tables(self.handle, int(bool(enable))), self.handle, "lumacu_set_pq_tables")
+
     def set_host_bands(self, bands: int) -> None:
         """Row bands per host-pointer call (0 = automatic)."""
         check(self._lib.lumacu_set_host_bands(self.handle, int(bands)), self.handle, "lumacu_set_host_bands")

@@ -224,6 +224,55 @@ def test_screened_chroma_equals_exact_chain(lumalib, po, torch_cuda, cbits, sc):
             assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
 
 
+@pytest.mark.parametrize("lmax,sc", [(1e4, 1.0), (1000.0, 20.0)])
+def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc):
+    """CS_YCBCR tuned kernels read PQ decode and the outer power of PQ encode from exhaustive device-built tables
+    (luma_pq_tables.cuh).  Same bits as the same kernels evaluating every powf per pixel (lumacu_set_pq_tables(0)), on
+    dense content: 18 decades of input incl. specials for encode; every combination class of 10-bit codes (uniform
+    random planes, incl. out-of-range codes) for decode; and one frame against the CPU oracle (host libm)."""
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+
+    w, h, n = 1920, 1080, 4
+    t = DeviceTransform(0, ptf="PQ", ptfBitDepth=10, colorSpace="YCBCR", colorBitDepth=10, maxLum=lmax, minLum=0.01, preScaling=sc)
+    ctx = t.quant.ctx
+    rng = np.random.default_rng(int(lmax))
+    frames = [po.noise_frame(w, h, seed=60 + i) / np.float32(sc) for i in range(n - 1)]
+    wide = np.power(np.float32(10.0), rng.uniform(-12.0, 6.0, size=(3, h, w)).astype(np.float32)).astype(np.float32)
+    wide.reshape(-1)[rng.integers(0, wide.size, 5000)] = rng.choice(
+        np.array([0.0, -1.0, np.inf, np.nan, 1e-45, 1e-38, 1e4, 1e-10, 3e38], np.float32), 5000)
+    frames.append(wide)
+    rgb = torch.from_numpy(np.stack(frames)).cuda()
+    ctx.set_pq_tables(False)
+    ref_planes = [p.clone() for p in t.encode(rgb)]
+    assert ctx.last_kernel_path == 1
+    ctx.set_pq_tables(True)
+    got = t.encode(rgb)
+    for p, (a, b) in enumerate(zip(got, ref_planes)):
+        assert torch.equal(a, b), f"encode: plane {p} differs in {(a != b).sum().item()} bytes"
+    # decode: uniform random 16-bit words, mostly within the 10-bit range
+    planes = t.alloc_planes(n, w, h)
+    for pl, (pw, ph) in zip(planes, po.plane_dims(w, h, 2)):
+        codes = rng.integers(0, 1024, size=(n, ph, pw), dtype=np.uint16)
+        wild = rng.random((n, ph, pw)) < 0.001
+        codes[wild] = rng.integers(0, 65536, size=int(wild.sum()), dtype=np.uint16)
+        pl[:, :, : pw * 2] = torch.from_numpy(codes.astype("<u2").view(np.uint8).reshape(n, ph, pw * 2)).cuda()
+    ctx.set_pq_tables(False)
+    ref_out = t.decode(planes, w, h).clone()
+    ctx.set_pq_tables(True)
+    out = t.decode(planes, w, h)
+    a, b = out.view(torch.int32), ref_out.view(torch.int32)
+    same = (a == b) | (torch.isnan(out) & torch.isnan(ref_out))
+    assert bool(same.all()), f"decode: {(~same).sum().item()} floats differ"
+    # the host libm's word on one frame of each
+    o = po.Oracle().setQuantizer("PQ", 10, "YCBCR", 10, lmax, 0.01)
+    cpu_planes, _ = o.encode(frames[0].copy(), 2, sc)
+    for a, b, (pw, ph) in zip(got, cpu_planes, po.plane_dims(w, h, 2)):
+        assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
+    cpu_out = o.decode([p[1].cpu().numpy() for p in planes], w, h, 2, sc)
+    assert bits_equal(out[1].cpu().numpy(), cpu_out)
+
+
 def test_plain_c_example_round_trips(torch_cuda):
     """examples/roundtrip.c (strict C99 against include/lumacu.h) encodes and decodes a frame on the GPU."""
     import shutil
