@@ -29,7 +29,8 @@ LUMA_DECL_GENERIC(3)
  * configuration in a few more for the tuning sweep.
  * Return NULL when there is no instantiation for the request. */
 constexpr int kEncVariantPlain = 4, kDecVariantPlain = 4;
-constexpr int kEncVariantScreened = 6; /* Lu'v' 4:2:0: plain loads + screened chroma (luma_fast.cuh FASTC) */
+constexpr int kEncVariantPrefetch = 24; /* plain kernel + L2 prefetch of the next tile (luma_fast.cuh PF 2) */
+constexpr int kEncVariantScreened = 67; /* Lu'v' 4:2:0: screened chroma, queued redo, L2 prefetch two tiles ahead (luma_fast.cuh FASTC 2, PF 6) */
 constexpr unsigned kEncStagedSmemBytes = 6u * 512u * 8u; /* luma_fast.cuh kEncStageBlock */
 #define LUMA_DECL_FAST(CSV)                                          \
     enc_fn get_encode_fast_cs##CSV(bool sub, int bytes, int walk, int variant, bool prescale); \

@@ -134,7 +134,7 @@ void launch_display_linear(unsigned blocks, unsigned n_frames, cudaStream_t st, 
  * Every configuration exists as variant 4 (PF 0, the default); the headline instantiation (Lu'v', 4:2:0,
  * 16-bit planes, walk 1) is additionally compiled in more variants so that scripts/sweep.py can re-measure
  * the choice. */
-template <bool SUB, int BYTES, int PF, bool PRESC, bool FASTC>
+template <bool SUB, int BYTES, int PF, bool PRESC, int FASTC>
 static enc_fn pick_walk(int walk)
 {
 #if LUMA_TU_CS == 0 || LUMA_TU_CS == 3
@@ -163,25 +163,38 @@ static enc_fn pick_enc_cfg(bool sub, int bytes, int walk, bool screened)
 {
 #if LUMA_TU_CS == 0
     if (sub && screened) /* Lu'v' 4:2:0 with screened chroma (luma_fast.cuh FASTC) */
-        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, true>(walk) : pick_walk<true, 1, PF, PRESC, true>(walk);
+        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, 2>(walk) : pick_walk<true, 1, PF, PRESC, 2>(walk);
 #endif
     (void)screened;
     if (sub)
-        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, false>(walk) : pick_walk<true, 1, PF, PRESC, false>(walk);
-    return bytes == 2 ? pick_walk<false, 2, PF, PRESC, false>(walk) : pick_walk<false, 1, PF, PRESC, false>(walk);
+        return bytes == 2 ? pick_walk<true, 2, PF, PRESC, 0>(walk) : pick_walk<true, 1, PF, PRESC, 0>(walk);
+    return bytes == 2 ? pick_walk<false, 2, PF, PRESC, 0>(walk) : pick_walk<false, 1, PF, PRESC, 0>(walk);
 }
 
 enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk, int variant, bool prescale)
 {
-    if (variant == 4 || variant == kEncVariantScreened) {
-        const bool scr = variant == kEncVariantScreened;
-        return prescale ? pick_enc_cfg<0, true>(sub, bytes, walk, scr) : pick_enc_cfg<0, false>(sub, bytes, walk, scr);
-    }
+    if (variant == 4)
+        return prescale ? pick_enc_cfg<0, true>(sub, bytes, walk, false) : pick_enc_cfg<0, false>(sub, bytes, walk, false);
+    if (variant == kEncVariantPrefetch) /* plain kernel + L2 prefetch of the thread's next tile */
+        return prescale ? pick_enc_cfg<2, true>(sub, bytes, walk, false) : pick_enc_cfg<2, false>(sub, bytes, walk, false);
+    if (variant == kEncVariantScreened) /* Lu'v' 4:2:0: screened chroma, queued redo, L2 prefetch two tiles ahead */
+        return prescale ? pick_enc_cfg<6, true>(sub, bytes, walk, true) : pick_enc_cfg<6, false>(sub, bytes, walk, true);
     if (prescale)
         return nullptr; /* the tuning variants exist for preScaling == 1 only */
 #if LUMA_TU_CS == 0
     if (sub && bytes == 2 && walk == 0) {
         switch (variant) {
+        /* screened chroma (the default is 67): 6 = warp-wide redo, 7 = queued redo, 26 / 27 = those + L2 prefetch of the
+         * next tile, 67 = queued + prefetch two tiles ahead, 86 / 87 = tensor-map staging.  Sustained encode of 32 4K
+         * frames on B200 (scripts/sweep.py --preroll 0.6, profiles/r02_sweep_screened.log): exact chain 740 us, 6: 714,
+         * 7: 721, 26: 689, 27: 669, 86: 675, 87: 670, 67: 660 (decode: 654) */
+        case 6: return encode_fast_kernel<kCS, true, 2, 0, 0, 4, false, 1>;
+        case 7: return encode_fast_kernel<kCS, true, 2, 0, 0, 4, false, 2>;
+        case 26: return encode_fast_kernel<kCS, true, 2, 0, 2, 4, false, 1>;
+        case 27: return encode_fast_kernel<kCS, true, 2, 0, 2, 4, false, 2>;
+        case 86: return encode_fast_kernel<kCS, true, 2, 0, 8, 4, false, 1>;
+        case 87: return encode_fast_kernel<kCS, true, 2, 0, 8, 4, false, 2>;
+        case 64: return encode_fast_kernel<kCS, true, 2, 0, 6, 4>; /* exact chain + prefetch two tiles ahead */
         case 3: return encode_fast_kernel<kCS, true, 2, 0, 0, 3>;
         case 5: return encode_fast_kernel<kCS, true, 2, 0, 0, 5>;
         case 84: return encode_fast_kernel<kCS, true, 2, 0, 8, 4>; /* tensor-map staging */

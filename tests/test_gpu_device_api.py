@@ -127,7 +127,8 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
     cpu_planes, _ = o.encode(rgb[0].cpu().numpy().copy(), 2, 1.0)
     for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
         assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
-    for enc_v, dec_v, cap in [(4, 0, 0), (6, 0, 0), (1006, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
+    for enc_v, dec_v, cap in [(4, 0, 0), (24, 0, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
+                              (87, 0, 0), (1067, 0, 0), (1024, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
                               (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
         ctx.set_tuning(enc_v, dec_v, cap)
         planes = t.encode(rgb)
@@ -208,7 +209,7 @@ def test_screened_chroma_equals_exact_chain(lumalib, po, torch_cuda, cbits, sc):
     ctx.set_tuning(4)
     exact = [p.clone() for p in t.encode(rgb)]
     assert ctx.last_kernel_path == 1
-    for tune in (0, 6, 1006):  # default (= screened), screened explicitly, screened + bucket/threshold luma search
+    for tune in (0, 67, 27, 6, 7, 26, 86, 87, 1067):  # default (= screened), the screened variants (queued redo, L2 prefetch, TMA staging), screened + bucket/threshold luma search
         ctx.set_tuning(tune)
         got = t.encode(rgb)
         assert ctx.last_kernel_path == 1
