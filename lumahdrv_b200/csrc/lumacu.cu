@@ -703,7 +703,11 @@ try {
              * (B) just the thresholds' own range plus a bucket either side: smaller, needs both clamps on the device
              *     (LUTs such as LOG-12 whose buckets are too fine for (A) to fit in shared memory, and every
              *     ordered-key table). */
-            uint32_t lo = (k_lo >> S) - 1u, hi = k_hi >> S;
+            /* (A) ends one bucket above the last threshold: everything beyond it has the code max_val anyway, and the
+             * device's upper key clamp (needed for NaN) folds it onto that bucket -- for PQ-11 with Lmax = 1e4 this
+             * drops the 13 binades up to 1e8 (40.8 -> 27.6 KB staged per block) */
+            uint32_t lo = (k_lo >> S) - 1u, hi = std::min(k_hi >> S, (t_last >> S) + 1u);
+            const bool trimmed = hi < (k_hi >> S);
             bool clamp_lo = false;
             if (!raw_keys || t_last > k_hi || (size_t)(hi - lo + 1u) * 4 > 48 * 1024) {
                 lo = (t_first >> S) - 1u;
@@ -727,7 +731,7 @@ try {
             d_shift = S;
             d_lo = lo;
             d_lo_key = clamp_lo ? (lo << S) : 0u;
-            d_hi_key = clamp_lo ? (((hi + 1u) << S) - 1u) : k_hi;
+            d_hi_key = (clamp_lo || trimmed) ? (((hi + 1u) << S) - 1u) : k_hi;
             dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u); /* the kernels stage it with 128-bit loads */
         }
     }
