@@ -29,6 +29,7 @@ LUMA_DECL_GENERIC(3)
  * configuration in a few more for the tuning sweep.
  * Return NULL when there is no instantiation for the request. */
 constexpr int kEncVariantPlain = 4, kDecVariantPlain = 4;
+constexpr int kDecVariantPrefetch = 24; /* decode: plain loads + L2 prefetch of the next tile (luma_fast.cuh PF 2) */
 constexpr int kEncVariantPrefetch = 24; /* plain kernel + L2 prefetch of the next tile (luma_fast.cuh PF 2) */
 constexpr int kEncVariantScreened = 67; /* Lu'v' 4:2:0: screened chroma, queued redo, L2 prefetch two tiles ahead (luma_fast.cuh FASTC 2, PF 6) */
 constexpr unsigned kEncStagedSmemBytes = 6u * 512u * 8u; /* luma_fast.cuh kEncStageBlock */
@@ -53,6 +54,9 @@ const void *quantize_kernel_ptr();
 constexpr size_t kPqTabPqdBytes = (size_t)((0x3F800000u - 0x3B800000u + 1u + 31u) / 32u) * 16u;
 constexpr size_t kPqTabPqeBytes = (size_t)(0x3F8147AEu - 0x3F55C28Fu + 1u) * 4u;
 void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *pqe, float l_max);
+/* v-keyed luma search table of CS_YCBCR encode: kVdTabBytes of device memory + one flag word (non-zero = unusable) */
+constexpr size_t kVdTabBytes = (size_t)((((0x3F800000u >> 13) - (0x3D000000u >> 13) + 1u) + 3u) & ~3u) * 4u;
+void launch_build_vdtab(cudaStream_t st, const QuantDev &q, uint32_t *tab, uint32_t *bad, float l_max);
 void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
 void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);
 void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,

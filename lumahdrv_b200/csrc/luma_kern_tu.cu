@@ -65,6 +65,10 @@ void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *
     build_pqd_kernel<<<blocks, 256, 0, st>>>((uint4 *)pqd, l_max);
     build_pqe_kernel<<<blocks, 256, 0, st>>>(pqe);
 }
+void launch_build_vdtab(cudaStream_t st, const QuantDev &q, uint32_t *tab, uint32_t *bad, float l_max)
+{
+    build_vdtab_kernel<<<(kVdEntries + 255u) / 256u, 256, 0, st>>>(q, tab, bad, l_max);
+}
 #endif
 
 #if LUMA_TU_CS == 1
@@ -146,6 +150,13 @@ static enc_fn pick_walk(int walk)
 #endif
     if (walk == -1) /* direct search table over the thresholds' own range (both clamps on the device) */
         return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4, PRESC, FASTC>;
+#if LUMA_TU_CS == 2
+    if (walk == -2) /* CS_YCBCR: plane 0 searched by v = (219 y' + 16)/255 in the v-keyed table (no statistics) */
+        return encode_fast_kernel<kCS, SUB, BYTES, -2, PF, 4, PRESC, FASTC>;
+#else
+    if (walk == -2)
+        return nullptr;
+#endif
 #if LUMA_TU_CS == 0
     /* the headline colour space gets the exact walk length */
     if (walk <= 1)
@@ -224,11 +235,17 @@ dec_fn LUMA_CAT(get_decode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int variant
             return bytes == 2 ? decode_fast_kernel<kCS, true, 2, 0, 4> : decode_fast_kernel<kCS, true, 1, 0, 4>;
         return bytes == 2 ? decode_fast_kernel<kCS, false, 2, 0, 4> : decode_fast_kernel<kCS, false, 1, 0, 4>;
     }
+    if (variant == kDecVariantPrefetch) { /* the default: + L2 prefetch of the next tile's code words (656 -> 644 us per 32 4K frames) */
+        if (sub)
+            return bytes == 2 ? decode_fast_kernel<kCS, true, 2, 2, 4> : decode_fast_kernel<kCS, true, 1, 2, 4>;
+        return bytes == 2 ? decode_fast_kernel<kCS, false, 2, 2, 4> : decode_fast_kernel<kCS, false, 1, 2, 4>;
+    }
 #if LUMA_TU_CS == 0
     if (sub && bytes == 2) {
         switch (variant) {
         case 3: return decode_fast_kernel<kCS, true, 2, 0, 3>;
         case 5: return decode_fast_kernel<kCS, true, 2, 0, 5>;
+        case 64: return decode_fast_kernel<kCS, true, 2, 6, 4>; /* L2 prefetch two tiles ahead */
         case 13: return decode_fast_kernel<kCS, true, 2, 1, 3>;
         case 14: return decode_fast_kernel<kCS, true, 2, 1, 4>;
         case 15: return decode_fast_kernel<kCS, true, 2, 1, 5>;

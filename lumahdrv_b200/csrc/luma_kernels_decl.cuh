@@ -41,6 +41,9 @@ struct QuantDev {
      * of the outer power of PQ encode (one entry per float in [0.835, 1.01]); luma_pq_tables.cuh.  NULL = evaluate. */
     const uint4 *pqd;
     const float *pqe;
+    /* CS_YCBCR encode: direct search table keyed on v = (219 y' + 16)/255 (kVdEntries entries, luma_pq_tables.cuh (3));
+     * NULL when it could not be built for this LUT */
+    const uint32_t *vdtab;
 };
 
 constexpr int kThreads = 256;

@@ -34,6 +34,20 @@ constexpr uint32_t kPqdBuckets = (kPqdKeys + 31u) / 32u;
 constexpr uint32_t kPqeKey0 = 0x3F55C28Fu;                /* 0.835f */
 constexpr uint32_t kPqeKeys = 0x3F8147AEu - kPqeKey0 + 1u; /* ... 1.01f inclusive */
 
+/* (3) forward path, luma: code = quantize(PQdec(v), 0) with v = (219 y' + 16)/255 is a monotone step function of the float
+ *     v with one step per code (1023 of them for HDR10).  vdtab is a direct search table keyed on the bits of v, in the
+ *     format of the luminance-keyed one (luma_fast.cuh DirectSearch): buckets of 2^13 consecutive floats over
+ *     [2^-5, 1], at most one step per bucket, 20 KB of shared memory -- the luma code of a pixel costs a clamp, a shift, a
+ *     shared-memory read and an add instead of an L2 lookup of PQdec(v) plus the luminance search.  Built on the device
+ *     from the exact pieces (pqd / powf_glibc + the quantizer's own search), each step located by bisection and its
+ *     neighbourhood checked for strict monotonicity; if anything is irregular (two steps in a bucket: more than ~10
+ *     luma bits; a non-monotonic neighbourhood) the table is not used. */
+constexpr uint32_t kVdShift = 13u;
+constexpr uint32_t kVdLoBucket = 0x3D000000u >> kVdShift; /* 2^-5 */
+constexpr uint32_t kVdHiBucket = 0x3F800000u >> kVdShift; /* 1.0: the last bucket starts exactly there */
+constexpr uint32_t kVdBuckets = kVdHiBucket - kVdLoBucket + 1u;
+constexpr uint32_t kVdEntries = (kVdBuckets + 3u) & ~3u; /* staged 16 bytes at a time */
+
 /* the tail of transformPQ(decode) once Vp is known (src/luma_quantizer.cpp:498-499) */
 __device__ __forceinline__ float pq_decode_from_vp(float Vp, float l_max)
 {
@@ -140,5 +154,105 @@ static __device__ __noinline__ float3 ycbcr_inverse_px_tab(const QuantDev &q, fl
     o.z = pq_decode_tab(q, blue, l_max);
     return o;
 }
+
+/* Pixel PAIRS: the two pixels' table lookups (3 + 1 each on the forward path, 3 each on the inverse path) are all in
+ * flight together, which is what hides the L2 latency of the gathers; same expressions, evaluated per pixel. */
+struct Float3x2 {
+    float3 a, b;
+};
+/* LUMA_V: return v = (219 y' + 16)/255 itself in .x (the caller searches it in vdtab) instead of PQdec(v) */
+template <bool LUMA_V>
+static __device__ __noinline__ Float3x2 ycbcr_forward_px2_tab(const QuantDev &q, float3 p0, float3 p1, float l_max)
+{
+    const float Rp0 = pq_encode_tab(q, max_nan(p0.x, 1e-10f), l_max), Rp1 = pq_encode_tab(q, max_nan(p1.x, 1e-10f), l_max);
+    const float Gp0 = pq_encode_tab(q, max_nan(p0.y, 1e-10f), l_max), Gp1 = pq_encode_tab(q, max_nan(p1.y, 1e-10f), l_max);
+    const float Bp0 = pq_encode_tab(q, max_nan(p0.z, 1e-10f), l_max), Bp1 = pq_encode_tab(q, max_nan(p1.z, 1e-10f), l_max);
+    const float y0 = dot3(0.2627f, 0.6780f, 0.0593f, Rp0, Gp0, Bp0), y1 = dot3(0.2627f, 0.6780f, 0.0593f, Rp1, Gp1, Bp1);
+    const float v0 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y0), 16.0f), 255.0f);
+    const float v1 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y1), 16.0f), 255.0f);
+    Float3x2 c;
+    c.a.x = LUMA_V ? v0 : pq_decode_tab(q, v0, l_max);
+    c.b.x = LUMA_V ? v1 : pq_decode_tab(q, v1, l_max);
+    c.a.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp0, y0), 1.8814f)), 128.0f), 255.0f);
+    c.a.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp0, y0), 1.4746f)), 128.0f), 255.0f);
+    c.b.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp1, y1), 1.8814f)), 128.0f), 255.0f);
+    c.b.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp1, y1), 1.4746f)), 128.0f), 255.0f);
+    return c;
+}
+
+static __device__ __noinline__ Float3x2 ycbcr_inverse_px2_tab(const QuantDev &q, float2 y, float2 ca, float2 cb, float l_max)
+{
+    float v[6];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float yy = i ? y.y : y.x;
+        const float blue = __fadd_rn(yy, i ? ca.y : ca.x);
+        const float red = __fadd_rn(yy, i ? cb.y : cb.x);
+        const float green = __fdiv_rn(__fsub_rn(__fsub_rn(yy, __fmul_rn(0.2627f, red)), __fmul_rn(0.0593f, blue)), 0.6780f);
+        v[3 * i + 0] = clamp01_std(red);
+        v[3 * i + 1] = clamp01_std(green);
+        v[3 * i + 2] = clamp01_std(blue);
+    }
+    /* A lookup costs one 32-byte L2 sector; on content without locality (noise) three of them per pixel saturate the
+     * L2 (~235 G sectors/s on B200: 79 kMpx/s) while the SMs idle.  So the green of every other pixel is EVALUATED (two
+     * exact powf, ~220 instructions) instead of looked up: both resources busy.  Measured on 4K noise, decode:
+     * 1.19 TB/s-equivalent all looked up, 1.26 with every green evaluated, 1.29 with every other one. */
+    float o[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (i == 1 && q.pqd) /* green of the first pixel of the pair */
+            o[i] = (v[i] == 0.0f) ? __fmul_rn(l_max, 0.0f) : pq_decode(v[i], l_max);
+        else
+            o[i] = pq_decode_tab(q, v[i], l_max);
+    }
+    Float3x2 r;
+    r.a = make_float3(o[0], o[1], o[2]);
+    r.b = make_float3(o[3], o[4], o[5]);
+    return r;
+}
+
+#ifdef LUMA_PQ_TABLE_BUILDERS
+/* vdtab: one thread per bucket of 2^13 floats */
+__device__ __forceinline__ uint32_t vd_code(const QuantDev &q, const SearchCtx &s, uint32_t key, float l_max)
+{
+    return search_code<false>(s, pq_decode_tab(q, __uint_as_float(key), l_max));
+}
+__global__ void __launch_bounds__(256) build_vdtab_kernel(const QuantDev q, uint32_t *tab, uint32_t *bad, float l_max)
+{
+    powf_tables_stage();
+    SearchCtx s;
+    s.thr = q.thr, s.bucket = q.bucket, s.lut = q.lut;
+    s.max_val = q.max_val, s.shift = q.shift, s.base = q.base, s.nbm1 = q.nbm1, s.walk = q.walk, s.mode = q.search_mode;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < kVdEntries; b += gridDim.x * blockDim.x) {
+        if (b >= kVdBuckets) {
+            tab[b] = 0u;
+            continue;
+        }
+        const uint32_t kb = kVdLoBucket + b, k0 = kb << kVdShift, k1 = k0 + (1u << kVdShift) - 1u;
+        const uint32_t c_first = vd_code(q, s, k0, l_max), c_last = vd_code(q, s, k1, l_max);
+        uint32_t thr_low = 1u << kVdShift;
+        bool ok = c_last == c_first || c_last == c_first + 1u;
+        if (b + 1u < kVdBuckets && vd_code(q, s, k1 + 1u, l_max) < c_last)
+            ok = false; /* codes must not decrease across the bucket boundary */
+        if (ok && c_last != c_first) {
+            uint32_t lo = k0, hi = k1; /* code(lo) < c_last <= code(hi) */
+            while (hi - lo > 1u) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (vd_code(q, s, mid, l_max) >= c_last)
+                    hi = mid;
+                else
+                    lo = mid;
+            }
+            /* glibc's powf may round non-monotonically within a few floats of a step of Vp: the step must be clean */
+            for (uint32_t d = 1; d <= 96u && ok; ++d)
+                ok = vd_code(q, s, hi - d, l_max) < c_last && vd_code(q, s, hi + d - 1u, l_max) >= c_last;
+            thr_low = hi - k0;
+        }
+        if (!ok)
+            atomicOr(bad, 1u);
+        tab[b] = (c_first << 16) + 0x10000u - thr_low - (kb << kVdShift);
+    }
+}
+#endif /* LUMA_PQ_TABLE_BUILDERS */
 
 } // namespace lumacu

@@ -104,6 +104,7 @@ struct lumacu_ctx {
     std::vector<float> h_lut;
     DeviceBuffer d_tables; /* lut | thr | bucket | ctab | dtab | ylut */
     DeviceBuffer d_pq;       /* CS_YCBCR: pqd | pqe (luma_pq_tables.cuh), built on the device for pq_lmax */
+    DeviceBuffer d_vd;       /* CS_YCBCR: v-keyed luma search table + flag word, rebuilt with every quantizer */
     float pq_lmax = 0.0f;
     bool pq_valid = false, pq_off = false; /* pq_off: tests / sweeps run the tuned kernels without the tables */
     size_t tables_bytes = 0; /* bytes of d_tables in use (what lumacu_broadcast_quantizer copies to the peers) */
@@ -528,7 +529,7 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_out)
         cudaStreamSynchronize(ctx->s_out); /* an asynchronous call the caller never waited for */
-    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
+    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
                             &ctx->d_aux})
         if (b->p)
             cudaFree(b->p);
@@ -615,6 +616,46 @@ try {
 LUMACU_CATCH(nullptr)
 
 /* ================================ quantizer ========================================== */
+
+/* CS_YCBCR: the device-built tables of the tuned kernels (luma_pq_tables.cuh) for the quantizer `q` (whose LUT, thresholds
+ * and search tables are already in device memory): the two PQ tables depend on Lmax only and are kept across
+ * quantizers; the v-keyed luma search table is rebuilt every time.  Fills q.pqd / q.pqe / q.vdtab (NULL = the kernels
+ * evaluate that piece per pixel).  ~1 ms. */
+static int build_ycbcr_tables(lumacu_ctx *ctx, QuantDev &q, float max_lum)
+{
+    q.pqd = nullptr, q.pqe = nullptr, q.vdtab = nullptr;
+    if (!ctx->pq_valid || memcmp(&ctx->pq_lmax, &max_lum, sizeof(float)) != 0) {
+        ctx->pq_valid = false;
+        if (reserve(ctx, ctx->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) != LUMACU_OK) {
+            ctx->err.clear(); /* no room for the tables: PQ is evaluated per pixel instead */
+            return LUMACU_OK;
+        }
+        launch_build_pq_tables((unsigned)ctx->sm_count * 8u, ctx->stream, ctx->d_pq.p,
+                               (float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes), max_lum);
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 2;
+        ctx->pq_lmax = max_lum;
+        ctx->pq_valid = true;
+    }
+    q.pqd = (const uint4 *)ctx->d_pq.p;
+    q.pqe = (const float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes);
+    if (reserve(ctx, ctx->d_vd, kVdTabBytes + 16) != LUMACU_OK) {
+        ctx->err.clear();
+        return LUMACU_OK;
+    }
+    uint32_t *flag = (uint32_t *)((unsigned char *)ctx->d_vd.p + kVdTabBytes);
+    CU_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    launch_build_vdtab(ctx->stream, q, (uint32_t *)ctx->d_vd.p, flag, max_lum);
+    CU_TRY(ctx, cudaGetLastError());
+    uint32_t bad = 1;
+    CU_TRY(ctx, cudaMemcpyAsync(&bad, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches++;
+    if (!bad)
+        q.vdtab = (const uint32_t *)ctx->d_vd.p;
+    return LUMACU_OK;
+}
 
 extern "C" int lumacu_set_quantizer(lumacu_ctx *ctx, const float *lut, uint32_t lut_len, uint32_t max_val_color,
                                     int color_space, float max_lum)
@@ -774,22 +815,6 @@ try {
     if (!ylut.empty())
         CU_TRY(ctx, cudaMemcpy(d + off_ylut, ylut.data(), ylut.size() * 4, cudaMemcpyHostToDevice));
 
-    /* CS_YCBCR: exhaustive PQ tables for the tuned kernels, (re)built on the device when Lmax changes (~1 ms) */
-    if (color_space == CS_YCBCR && (!ctx->pq_valid || memcmp(&ctx->pq_lmax, &max_lum, sizeof(float)) != 0)) {
-        ctx->pq_valid = false;
-        if (reserve(ctx, ctx->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) == LUMACU_OK) {
-            launch_build_pq_tables((unsigned)ctx->sm_count * 8u, ctx->stream, ctx->d_pq.p,
-                                   (float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes), max_lum);
-            CU_TRY(ctx, cudaGetLastError());
-            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->launches += 2;
-            ctx->pq_lmax = max_lum;
-            ctx->pq_valid = true;
-        } else {
-            ctx->err.clear(); /* no room for the tables: the kernels evaluate PQ per pixel instead */
-        }
-    }
-
     QuantDev q{};
     q.lut = (const float *)d;
     q.thr = (const uint32_t *)(d + off_thr);
@@ -802,10 +827,6 @@ try {
     q.d_lo_key = d_lo_key;
     q.d_hi_key = d_hi_key;
     q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
-    if (color_space == CS_YCBCR && ctx->pq_valid) {
-        q.pqd = (const uint4 *)ctx->d_pq.p;
-        q.pqe = (const float *)((unsigned char *)ctx->d_pq.p + kPqTabPqdBytes);
-    }
     q.max_val = max_val;
     q.max_val_color = max_val_color;
     q.max_val_f = (float)max_val;
@@ -836,6 +857,9 @@ try {
     /* (the tuned search also wants every threshold to be a positive float: key > key(+0)) */
     ctx->fast_enc_ok = (mode == SEARCH_BUCKET && smem_enc != 0 && thr[0] > 0x80000000u);
     ctx->smem_dec_fast = smem_dec_fast;
+
+    if (color_space == CS_YCBCR && (rc = build_ycbcr_tables(ctx, q, max_lum)) != LUMACU_OK)
+        return rc;
 
     ctx->q = q;
     ctx->tables_bytes = total;
@@ -894,25 +918,10 @@ try {
         q.ctab = (const float *)rebase(q.ctab);
         q.dtab = (const uint32_t *)rebase(q.dtab);
         q.ylut = (const float *)rebase(q.ylut);
-        q.pqd = nullptr, q.pqe = nullptr;
-        if (src->color_space == CS_YCBCR && src->pq_valid) { /* built on the spot by the same deterministic kernels */
-            if (!dst->pq_valid || memcmp(&dst->pq_lmax, &src->pq_lmax, sizeof(float)) != 0) {
-                dst->pq_valid = false;
-                if (reserve(dst, dst->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) == LUMACU_OK) {
-                    launch_build_pq_tables((unsigned)dst->sm_count * 8u, dst->stream, dst->d_pq.p,
-                                           (float *)((unsigned char *)dst->d_pq.p + kPqTabPqdBytes), src->pq_lmax);
-                    CU_TRY(dst, cudaGetLastError());
-                    CU_TRY(dst, cudaStreamSynchronize(dst->stream));
-                    dst->launches += 2;
-                    dst->pq_lmax = src->pq_lmax;
-                    dst->pq_valid = true;
-                }
-            }
-            if (dst->pq_valid) {
-                q.pqd = (const uint4 *)dst->d_pq.p;
-                q.pqe = (const float *)((unsigned char *)dst->d_pq.p + kPqTabPqdBytes);
-            }
-        }
+        q.pqd = nullptr, q.pqe = nullptr, q.vdtab = nullptr;
+        /* built on the spot by the same deterministic kernels rather than copied (45 MB) */
+        if (src->color_space == CS_YCBCR && (rc = build_ycbcr_tables(dst, q, src->max_lum)) != LUMACU_OK)
+            return rc;
         dst->q = q;
         dst->tables_bytes = src->tables_bytes;
         dst->max_lum = src->max_lum;
@@ -1088,7 +1097,7 @@ int make_rgb_tensor_map(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_
 
 /* Default variants of the tuned kernels, from the sweep on B200 (DESIGN.md "kernel tuning"). */
 constexpr int kEncDefaultVariant = kEncVariantPlain;
-constexpr int kDecDefaultVariant = kDecVariantPlain;
+constexpr int kDecDefaultVariant = kDecVariantPrefetch;
 
 inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
@@ -1182,7 +1191,7 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
     EncArgs a{};
     a.q = ctx->q;
     if (ctx->pq_off)
-        a.q.pqd = nullptr, a.q.pqe = nullptr;
+        a.q.pqd = nullptr, a.q.pqe = nullptr, a.q.vdtab = nullptr;
     a.rgb = d_rgb;
     a.rgb_out = d_rgb_out;
     a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
@@ -1226,6 +1235,10 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
         const bool direct = ctx->q.dtab && !ctx->no_direct;
         const int walk_direct = ctx->q.d_lo_key ? -1 : 0; /* -1: direct table that needs the lower clamp too */
         int walk = direct ? walk_direct : (int)ctx->q.walk;
+        /* CS_YCBCR without statistics: plane 0 is searched by v in the v-keyed table (-2) */
+        const bool v_keyed = ctx->color_space == CS_YCBCR && a.q.vdtab && !d_stats && !ctx->no_direct && variant == kEncVariantPlain;
+        if (v_keyed)
+            walk = -2;
         fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         if (!fn && direct) { /* tuning variants exist for one search flavour only */
             walk = (int)ctx->q.walk;
@@ -1237,7 +1250,7 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
             fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (fn && walk <= 0)
-            smem = (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
+            smem = walk == -2 ? kVdTabBytes : (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
         if (fn && staged && variant != kEncVariantPlain)
             smem += kEncStagedSmemBytes;
     }

@@ -127,7 +127,7 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
     cpu_planes, _ = o.encode(rgb[0].cpu().numpy().copy(), 2, 1.0)
     for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
         assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
-    for enc_v, dec_v, cap in [(4, 0, 0), (24, 0, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
+    for enc_v, dec_v, cap in [(4, 4, 0), (24, 24, 0), (0, 64, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
                               (87, 0, 0), (1067, 0, 0), (1024, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
                               (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
         ctx.set_tuning(enc_v, dec_v, cap)
@@ -251,6 +251,10 @@ def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc)
     got = t.encode(rgb)
     for p, (a, b) in enumerate(zip(got, ref_planes)):
         assert torch.equal(a, b), f"encode: plane {p} differs in {(a != b).sum().item()} bytes"
+    # without statistics plane 0 is searched by v = (219 y' + 16)/255 in the v-keyed table; with them, by luminance
+    with_stats = t.encode(rgb, stats=t.alloc_stats(n))
+    for p, (a, b) in enumerate(zip(with_stats, ref_planes)):
+        assert torch.equal(a, b), f"encode with statistics: plane {p} differs in {(a != b).sum().item()} bytes"
     # decode: uniform random 16-bit words, mostly within the 10-bit range
     planes = t.alloc_planes(n, w, h)
     for pl, (pw, ph) in zip(planes, po.plane_dims(w, h, 2)):
