@@ -89,7 +89,7 @@ def launches(tag: str, rnd: str):
     print("wrote", out.name, "and launch summary")
 
 
-def full(tag: str, rnd: str, frames: int = 8):
+def full(tag: str, rnd: str, frames: int = 32):
     rep = ROOT / "gpurun_out" / f"{tag}_prof.ncu-rep"
     if not rep.exists():
         return
@@ -122,7 +122,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
     ap.add_argument("--round", default="r01")
-    ap.add_argument("--frames", type=int, default=8, help="frames per launch of the profiled bench run")
+    ap.add_argument("--frames", type=int, default=32, help="frames per launch of the profiled bench run (scripts/gpu_profile.sh: 32)")
     a = ap.parse_args()
     (ROOT / "profiles").mkdir(exist_ok=True)
     launches(a.tag, a.round)
