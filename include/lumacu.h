@@ -29,6 +29,11 @@
  *    pinned buffers and return when the result is in host memory.  A NULL
  *    stream selects the context's own (non-blocking) stream; to launch on the
  *    CUDA default stream pass cudaStreamLegacy (0x1) or cudaStreamPerThread (0x2).
+ *  - a context is thread-compatible, not thread-safe: one host thread at a time, and ONE stream's worth of work in
+ *    flight per context -- the per-frame statistics workspace and the quantizer tables belong to the context, so two
+ *    launches of the same context on different caller streams must be ordered by the caller (use one context per
+ *    stream / thread / GPU instead; contexts are cheap).  lumacu_set_quantizer synchronises the whole device before it
+ *    replaces the tables.
  *  - results are bit-identical to the reference CPU path for the integer
  *    planes and for the decoded floats (see DESIGN.md for the one documented
  *    libm dependency: CS_YCBCR calls powf per pixel).

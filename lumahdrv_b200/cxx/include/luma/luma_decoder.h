@@ -100,7 +100,8 @@ private:
     vpx_image_t *m_vpxFrame;
     LumaDecoderParams m_params;
     bool m_firstFrame, m_haveCodec;
-    std::vector<unsigned char *> m_registered; /* page-locked libvpx frame buffers */
+    std::vector<unsigned char *> m_registered; /* page-locked libvpx frame buffers, least recently seen first */
+    size_t m_registeredBytes;                  /* size of each registered range (changes with the frame geometry) */
 };
 
 #endif // LUMA_DECODER_H

@@ -38,7 +38,7 @@ T read_as(const binary *bytes, size_t index = 0)
 } // namespace
 
 LumaDecoder::LumaDecoder(const char *inputFile, bool verbose)
-    : LumaDecoderBase(inputFile, verbose), m_vpxFrame(NULL), m_firstFrame(false), m_haveCodec(false)
+    : LumaDecoderBase(inputFile, verbose), m_vpxFrame(NULL), m_firstFrame(false), m_haveCodec(false), m_registeredBytes(0)
 {
     memset(&m_codec, 0, sizeof(m_codec));
     if (inputFile != NULL)
@@ -46,19 +46,39 @@ LumaDecoder::LumaDecoder(const char *inputFile, bool verbose)
 }
 
 /* libvpx hands out frames from a small pool of buffers it owns; page-lock each buffer the first time it is seen
- * (direct DMA instead of a staged copy).  LUMA_NO_REGISTER_VPX=1 disables it. */
+ * (direct DMA instead of a staged copy of the 3 B/px).  The buffers are libvpx's, so the registration is kept honest:
+ * everything is unregistered as soon as the frame geometry changes (libvpx reallocates its pool then), and at most 16
+ * ranges are held, the least recently seen one being dropped first -- a buffer libvpx no longer hands out does not
+ * stay page-locked for long.  LUMA_NO_REGISTER_VPX=1 disables registration altogether (staged copies, no pinning of
+ * memory this class does not own). */
 void LumaDecoder::registerPlanes()
 {
     static const bool off = getenv("LUMA_NO_REGISTER_VPX") && getenv("LUMA_NO_REGISTER_VPX")[0] != '0';
-    if (off || !m_vpxFrame || !m_vpxFrame->planes[0] || !m_vpxFrame->planes[2] || m_registered.size() >= 32)
+    if (off || !m_vpxFrame || !m_vpxFrame->planes[0] || !m_vpxFrame->planes[2])
         return;
     unsigned char *lo = m_vpxFrame->planes[0];
     const unsigned chromaRows = m_vpxFrame->y_chroma_shift ? (m_vpxFrame->d_h + 1) >> 1 : m_vpxFrame->d_h;
     unsigned char *hi = m_vpxFrame->planes[2] + (size_t)m_vpxFrame->stride[2] * chromaRows;
+    const size_t bytes = hi > lo ? (size_t)(hi - lo) : 0;
+    if (bytes != m_registeredBytes) { /* new geometry: libvpx has a new pool */
+        for (size_t i = 0; i < m_registered.size(); i++)
+            lumacu_host_unregister(m_registered[i]);
+        m_registered.clear();
+        m_registeredBytes = bytes;
+    }
     for (size_t i = 0; i < m_registered.size(); i++)
-        if (m_registered[i] == lo)
+        if (m_registered[i] == lo) { /* seen before: move to the back (most recently used) */
+            m_registered.erase(m_registered.begin() + (long)i);
+            m_registered.push_back(lo);
             return;
-    if (hi > lo && lumacu_host_register(lo, (size_t)(hi - lo)) == 0)
+        }
+    if (!bytes)
+        return;
+    if (m_registered.size() >= 16) {
+        lumacu_host_unregister(m_registered.front());
+        m_registered.erase(m_registered.begin());
+    }
+    if (lumacu_host_register(lo, bytes) == 0)
         m_registered.push_back(lo);
 }
 
