@@ -12,6 +12,8 @@
 #include "luma_decoder.h"
 
 #include "../../../include/lumacu.h"
+
+#include <chrono>
 #include "luma_exception.h"
 
 #include <cstdio>
@@ -196,8 +198,22 @@ bool LumaDecoder::run()
 
 LumaFrame *LumaDecoder::decode()
 {
+    static const bool timing = getenv("LUMA_FACADE_TIMING") && getenv("LUMA_FACADE_TIMING")[0] != '0';
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     if (!run())
         return NULL;
+    const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    struct Report { /* printed when decode() returns, whichever way */
+        bool on;
+        std::chrono::steady_clock::time_point a, b;
+        ~Report()
+        {
+            if (on)
+                fprintf(stderr, "facade-timing decode: run() (container + codec) %.3f ms, transform %.3f ms\n",
+                        std::chrono::duration<double, std::milli>(b - a).count(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count());
+        }
+    } report = {timing, t0, t1};
     if (m_frame.width != m_vpxFrame->d_w || m_frame.height != m_vpxFrame->d_h || !m_frame.buffer) {
         m_frame.width = m_vpxFrame->d_w;
         m_frame.height = m_vpxFrame->d_h;

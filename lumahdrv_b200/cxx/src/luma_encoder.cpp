@@ -12,6 +12,8 @@
 #include "luma_encoder.h"
 
 #include "../../../include/lumacu.h"
+
+#include <chrono>
 #include "luma_exception.h"
 
 #include <cstdio>
@@ -206,12 +208,22 @@ bool LumaEncoder::encode(LumaFrame *frame)
     lumacu_ctx *ctx = m_quant.device();
     lumacu_frame_stats st;
     const int32_t strides[3] = {m_rawFrame.stride[0], m_rawFrame.stride[1], m_rawFrame.stride[2]};
+    /* LUMA_FACADE_TIMING=1: where a call's time goes -- the transform (this library) or run() (codec + container) */
+    static const bool timing = getenv("LUMA_FACADE_TIMING") && getenv("LUMA_FACADE_TIMING")[0] != '0';
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     const int rc = lumacu_encode(ctx, frame->buffer, frame->width, frame->height, (int)m_params.profile,
                                  m_params.preScaling, m_rawFrame.planes, strides, m_strict ? 1 : 0, &st);
     if (rc != LUMACU_OK)
         throw_status(ctx, rc, "LumaEncoder::encode");
     meanLuminanceCheck(st.sum, (size_t)frame->width * frame->height);
-    return run();
+    if (!timing)
+        return run();
+    const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    const bool ok = run();
+    const std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "facade-timing encode: transform %.3f ms, run() (codec + container) %.3f ms\n",
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+    return ok;
 }
 
 bool LumaEncoder::run()
