@@ -98,6 +98,64 @@ def test_full_size_properties(lumalib, po, torch_cuda, w, h):
         assert st["max"][f] == pytest.approx(float(y.max()), rel=1e-5)
 
 
+@pytest.mark.parametrize("w,h,n", [(3840, 2160, 3), (7680, 4320, 2)])
+def test_whole_frames_of_a_batch_equal_the_oracle(lumalib, po, torch_cuda, w, h, n):
+    """Whole 4K / 8K noise frames through the multi-frame launch (the grid geometry bench.py times), every byte of every
+    plane and every decoded float of every frame against the CPU oracle, plus the per-frame statistics."""
+    torch = torch_cuda
+    from lumahdrv_b200.device import DeviceTransform
+    t = DeviceTransform(0)
+    frames = [po.noise_frame(w, h, seed=900 + i) for i in range(n)]
+    rgb = torch.from_numpy(np.stack(frames)).cuda()
+    stats = t.alloc_stats(n)
+    planes = t.encode(rgb, stats=stats)
+    assert t.quant.ctx.last_kernel_path == 1
+    dec = t.decode(planes, w, h)
+    st = t.stats_to_numpy(stats)
+    o = po.Oracle().setQuantizer("PQ", 11, "LUV", 8)
+    for f in range(n):
+        fc = frames[f].copy()
+        ref_planes, _ = o.encode(fc, 2, 1.0)
+        for p, (a, b, (pw, ph)) in enumerate(zip(planes, ref_planes, po.plane_dims(w, h, 2))):
+            assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2]), f"frame {f} plane {p}"
+        assert bits_equal(dec[f].cpu().numpy(), o.decode(ref_planes, w, h, 2, 1.0)), f"frame {f} decoded floats"
+        y = fc[0].astype(np.float64)
+        assert st["max"][f] == np.float32(y.max()) and st["min"][f] == np.float32(y.min())
+        assert st["sum"][f] == pytest.approx(float(y.sum()), rel=1e-9)
+
+
+def test_bench_line_carries_parity_and_configs(torch_cuda):
+    """bench.py on this GPU (2 frames per step, a few steps): ONE JSON line with the contract's keys, `parity` with zero
+    mismatches from the CPU checker on the benchmark's own data (device-resident and end-to-end arms), and the cfg2..cfg5
+    block, each configuration with its own zero-mismatch parity."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "3", "--warmup", "3", "--frames", "2", "--e2e-frames", "2",
+                        "--config-steps", "2", "--no-cpu-baseline", "--no-sustained"], capture_output=True, text=True, timeout=550)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "parity", "configs"):
+        assert k in d, k
+    assert d["gpu_launches"] == 6 and d["value"] > 0 and d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.2
+    for par in (d["parity"], d["e2e"]["parity"]):
+        assert par["plane_mismatch_bytes"] == 0 and par["max_ulp"] == 0 and par["frames_checked"] == 1 and par["ranks_failed"] == 0
+        assert par["pixels_checked"] == 3840 * 2160 and par["stats_max_mismatches"] == 0 and par["stats_sum_max_rel_err"] < 1e-6
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(d["configs"]) == {"cfg2", "cfg3", "cfg4", "cfg5"}
+    for name, c in d["configs"].items():
+        assert "error" not in c, (name, c)
+        assert c["value"] > 0 and c["parity"]["plane_mismatch_bytes"] == 0 and c["parity"]["max_ulp"] == 0, name
+    assert d["configs"]["cfg5"]["parity"]["stats_max_mismatches"] == 0
+    assert d["configs"]["cfg4"]["frames_total_per_step"] >= 64
+
+
 def test_luma_codes_are_fixed_points(lumalib, torch_cuda):
     """quantize(dequantize(code)) == code for every code of every shipped transfer function (exact property)."""
     import lumahdrv_b200 as L
