@@ -150,6 +150,8 @@ static enc_fn pick_walk(int walk)
 #endif
     if (walk == -1) /* direct search table over the thresholds' own range (both clamps on the device) */
         return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4, PRESC, FASTC>;
+    if (walk == -3) /* 64-bit direct table, two thresholds per bucket (wide LUTs such as PQ-12) */
+        return encode_fast_kernel<kCS, SUB, BYTES, -3, PF, 4, PRESC, FASTC>;
 #if LUMA_TU_CS == 2
     if (walk == -2) /* CS_YCBCR: plane 0 searched by v = (219 y' + 16)/255 in the v-keyed table (no statistics) */
         return encode_fast_kernel<kCS, SUB, BYTES, -2, PF, 4, PRESC, FASTC>;

@@ -777,6 +777,53 @@ try {
         }
     }
 
+    /* Wide LUTs (PQ-12, ...): no bucket width puts at most ONE threshold in a bucket within the shared-memory budget, but
+     * at most TWO works.  Same idea with 64-bit entries {A, B}:
+     *     A = (c0 << 16) + 0x10000 - t1 - (bucket << S),   B = 0x10000 - t2 - (bucket << S)
+     * (t1 <= t2 = offsets of the bucket's thresholds, 2^S when absent): code = ((A + key) >> 16) + ((B + key) >> 16) --
+     * one 64-bit shared-memory read and three adds per sample instead of a bucket head plus a four-threshold walk.
+     * Always used with both key clamps (luma_fast.cuh WALK -3). */
+    uint32_t d_double = 0;
+    if (dtab.empty() && mode == SEARCH_BUCKET && thr[0] > 0x80000000u && max_val >= 2u && max_val <= 32767u) {
+        const uint32_t k_lo = f2u(1e-4f);
+        const uint32_t t_first = thr[0] ^ flip, t_last = thr[max_val - 1] ^ flip;
+        for (uint32_t S = 16; S >= 12 && dtab.empty(); S--) {
+            bool ok = true;
+            for (uint32_t j = 2; j < max_val && ok; j++)
+                ok = ((thr[j] ^ flip) >> S) != ((thr[j - 2] ^ flip) >> S);
+            if (!ok)
+                continue;
+            uint32_t lo = (t_first >> S) - 1u, hi = (t_last >> S) + 1u;
+            if (raw_keys) /* searched values are clamped to >= 1e-4 (less an ulp): nothing below is ever asked.  The top
+                           * stays one bucket above the LAST threshold even beyond 1e8: NaN is folded there by the
+                           * upper key clamp and must come out as max_val */
+                lo = std::max(lo, (k_lo >> S) - 1u);
+            if (hi < lo || (size_t)(hi - lo + 1u) * 8 > 56 * 1024)
+                break; /* finer buckets only get bigger */
+            const uint32_t n = hi - lo + 1u;
+            dtab.resize((size_t)n * 2);
+            uint32_t j = 0;
+            for (uint32_t b = 0; b < n; b++) {
+                const uint32_t kb = lo + b;
+                while (j < max_val && ((thr[j] ^ flip) >> S) < kb)
+                    j++;
+                uint32_t t1 = 1u << S, t2 = 1u << S;
+                if (j < max_val && ((thr[j] ^ flip) >> S) == kb)
+                    t1 = (thr[j] ^ flip) - (kb << S);
+                if (j + 1 < max_val && ((thr[j + 1] ^ flip) >> S) == kb)
+                    t2 = (thr[j + 1] ^ flip) - (kb << S);
+                dtab[2 * b] = (j << 16) + 0x10000u - t1 - (kb << S);
+                dtab[2 * b + 1] = 0x10000u - t2 - (kb << S);
+            }
+            d_double = 1;
+            d_shift = S;
+            d_lo = lo;
+            d_lo_key = lo << S;
+            d_hi_key = ((hi + 1u) << S) - 1u;
+            dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u);
+        }
+    }
+
     /* CS_YCBCR decode: per-code y' = ((255 PQenc(lut[code])) - 16) / 219 with the reference's own float expression
      * (src/luma_quantizer.cpp:447-448, 493-494) and the host libm */
     std::vector<float> ylut;
@@ -824,6 +871,7 @@ try {
     q.d_shift = d_shift;
     q.d_lo = d_lo;
     q.d_n = (uint32_t)dtab.size();
+    q.d_double = d_double;
     q.d_lo_key = d_lo_key;
     q.d_hi_key = d_hi_key;
     q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
@@ -1232,8 +1280,12 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
             make_rgb_tensor_map(ctx, d_rgb, w, h, a.rgb_plane_stride, a.rgb_frame_stride, n_frames, a.rgb_tmap) != LUMACU_OK)
             variant = kEncVariantPlain;
         /* walk 0 = direct search table (one LDS per sample); otherwise bucket heads + <= walk threshold compares */
-        const bool direct = ctx->q.dtab && !ctx->no_direct;
-        const int walk_direct = ctx->q.d_lo_key ? -1 : 0; /* -1: direct table that needs the lower clamp too */
+        /* the 64-bit wide-LUT table (up to 56 KB: three resident blocks instead of four) pays off for the screened kernel,
+         * which is latency-bound (PQ-12 4:2:0: 6.2 vs 5.4 TB/s), not for the exact-chain kernels, which are pipe-bound and
+         * want the occupancy (PQ-12 4:4:4: 5.0 vs 5.65 TB/s with the bucket + threshold walk) */
+        const bool direct = ctx->q.dtab && !ctx->no_direct && (!ctx->q.d_double || variant == kEncVariantScreened);
+        /* -1: direct table that needs the lower clamp too; -3: 64-bit entries, two thresholds per bucket */
+        const int walk_direct = ctx->q.d_double ? -3 : (ctx->q.d_lo_key ? -1 : 0);
         int walk = direct ? walk_direct : (int)ctx->q.walk;
         /* CS_YCBCR without statistics: plane 0 is searched by v in the v-keyed table (-2) */
         const bool v_keyed = ctx->color_space == CS_YCBCR && a.q.vdtab && !d_stats && !ctx->no_direct && variant == kEncVariantPlain;

@@ -22,6 +22,8 @@ CONFIGS = [
     ("cfg4' 4K LOG-12 Lu'v' 12 p2", 3840, 2160, 32, dict(ptf="LOG", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=12, profile=2)),
     ("cfg5 8K PQ Lu'v' 11/8 p2 (+stats)", 7680, 4320, 8, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=8, profile=2)),
     ("4K PQ-12 Lu'v' 12 p3 (4:4:4)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=12, profile=3)),
+    ("4K PQ-12 Lu'v' 8 p2 (wide LUT, 4:2:0)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=8, profile=2)),
+    ("4K PQ-16 Lu'v' 8 p2 (-pb 16: binary search)", 3840, 2160, 8, dict(ptf="PQ", ptfBitDepth=16, colorSpace="LUV", colorBitDepth=8, profile=2)),
     ("4K PQ-11 XYZ p2", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="XYZ", colorBitDepth=8, profile=2)),
     ("4K PQ-11 RGB p2", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="RGB", colorBitDepth=8, profile=2)),
     ("1080p PQ-8 Lu'v' 8 p0 (8-bit 4:2:0)", 1920, 1080, 64, dict(ptf="PQ", ptfBitDepth=8, colorSpace="LUV", colorBitDepth=8, profile=0)),
@@ -36,6 +38,8 @@ def main():
         if only and only not in name:
             continue
         t = DeviceTransform(0, **kw)
+        if len(sys.argv) > 2:  # encoder tuning variant (lumacu_set_tuning), e.g. 1004 = bucket/threshold search instead of the direct tables
+            t.quant.ctx.set_tuning(int(sys.argv[2]), 0, 0)
         g = torch.Generator(device=dev).manual_seed(7)
         rgb = 0.005 * torch.pow(torch.tensor(2.0e6, device=dev), torch.rand((F, 3, h, w), generator=g, device=dev))
         planes = t.alloc_planes(F, w, h)
