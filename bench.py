@@ -248,14 +248,23 @@ def run_parity_check(params: dict, frame, planes, out) -> dict:
     import tempfile
 
     import numpy as np
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    need = 2 * (frame.nbytes + out.nbytes + sum(p.nbytes for p in planes)) + (64 << 20)
+    base = None  # RAM-backed /dev/shm when it has room for this rank's frame (it is small in some containers), else TMPDIR
+    try:
+        if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) and shutil.disk_usage("/dev/shm").free > 8 * need:
+            base = "/dev/shm"
+    except OSError:
+        base = None
     d = Path(tempfile.mkdtemp(prefix="luma_parity_", dir=base))
     try:
-        (d / "params.json").write_text(json.dumps(params))
-        np.save(d / "in.npy", frame)
-        for i, pl in enumerate(planes):
-            np.save(d / f"p{i}.npy", pl)
-        np.save(d / "out.npy", out)
+        try:
+            (d / "params.json").write_text(json.dumps(params))
+            np.save(d / "in.npy", frame)
+            for i, pl in enumerate(planes):
+                np.save(d / f"p{i}.npy", pl)
+            np.save(d / "out.npy", out)
+        except OSError as e:
+            return {"error": f"could not stage the frame for the checker in {d}: {e}"[:300]}
         r = subprocess.run([sys.executable, str(ROOT / "oracle" / "parity_check.py"), str(d)], capture_output=True, text=True)
         if r.returncode != 0:
             return {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else

@@ -29,6 +29,9 @@
  *    pinned buffers and return when the result is in host memory.  A NULL
  *    stream selects the context's own (non-blocking) stream; to launch on the
  *    CUDA default stream pass cudaStreamLegacy (0x1) or cudaStreamPerThread (0x2).
+ *  - the host-pointer entry points accept any host memory, but only page-locked memory (lumacu_host_alloc,
+ *    lumacu_host_register) moves at PCIe rate; pageable memory is staged by the driver, several times slower.  The
+ *    first time a context sees a pageable frame or plane buffer it says so on stderr (LUMACU_QUIET=1 silences it).
  *  - a context is thread-compatible, not thread-safe: one host thread at a time, and ONE stream's worth of work in
  *    flight per context -- the per-frame statistics workspace and the quantizer tables belong to the context, so two
  *    launches of the same context on different caller streams must be ordered by the caller (use one context per

@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda.h> /* CUtensorMap + enums only; the encoder entry point is resolved at run time */
@@ -128,6 +129,7 @@ struct lumacu_ctx {
     lumacu_frame_stats *pending_stats = nullptr; /* caller's stats to fill at lumacu_wait (NULL = none) */
     int pending_bands = 0;
     cudaEvent_t ev_input = nullptr; /* recorded after the last H2D copy of the call: the caller's input is reusable */
+    bool pageable_warned = false;   /* the one-time note about pageable caller memory has been printed */
 };
 
 static int finish_pending(lumacu_ctx *ctx);
@@ -1721,6 +1723,29 @@ static int finish_pending(lumacu_ctx *ctx)
     return LUMACU_OK;
 }
 
+/* The host-pointer entry points run at PCIe rate only from page-locked memory; with pageable memory the driver stages
+ * every copy through its own bounce buffer (several times slower, and the "asynchronous" copies block).  That is legal,
+ * so the call proceeds -- but not silently: once per context a note goes to stderr (the reference reports its own
+ * warnings there, src/luma_encoder.cpp:314-316), unless LUMACU_QUIET is set. */
+static void note_if_pageable(lumacu_ctx *ctx, const void *p, const char *what)
+{
+    if (ctx->pageable_warned)
+        return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeUnregistered)
+        return;
+    ctx->pageable_warned = true;
+    const char *q = getenv("LUMACU_QUIET");
+    if (q && q[0] && q[0] != '0')
+        return;
+    fprintf(stderr, "lumacu: %s is pageable host memory: copies are staged by the driver (slow). Allocate it with "
+                    "lumacu_host_alloc or page-lock it with lumacu_host_register. (LUMACU_QUIET=1 silences this note.)\n", what);
+}
+
 static int ensure_async_state(lumacu_ctx *ctx)
 {
     if (!ctx->h_pin) {
@@ -1748,6 +1773,8 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
         return rc;
+    note_if_pageable(ctx, rgb, "the frame passed to lumacu_encode");
+    note_if_pageable(ctx, planes[0], "the plane buffer passed to lumacu_encode");
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);
@@ -1830,6 +1857,8 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
         return rc;
+    note_if_pageable(ctx, rgb, "the frame passed to lumacu_decode");
+    note_if_pageable(ctx, planes[0], "the plane buffer passed to lumacu_decode");
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
     plane_geometry(w, h, profile, pw, ph);

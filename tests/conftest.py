@@ -11,6 +11,12 @@ if str(ROOT) not in sys.path:
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 
+# most tests hand plain (pageable) numpy arrays to the host-pointer API; the library's one-time note about that on
+# stderr is checked once (tests/test_gpu_host_staging.py) and silenced everywhere else
+import os  # noqa: E402
+
+os.environ.setdefault("LUMACU_QUIET", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -178,3 +178,42 @@ def test_broadcast_quantizer_and_async_pair_through_the_c_abi(lumalib, po):
         assert bits_equal(outs[i], o.decode(refs[i], w, h, 2, 1.0)), f"context {i}"
     for c in ctxs:
         c.close()
+
+
+def test_pageable_host_buffers_are_reported_once(lumalib):
+    """Pageable caller memory is legal but slow (the driver stages the copies): the first call that sees it says so on
+    stderr, once per context; page-locked buffers (lumacu_host_alloc / torch pin_memory) stay silent."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    prog = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import lumahdrv_b200 as L
+w, h = 256, 64
+enc = L.LumaEncoder(); enc.initialize(None, w, h)
+frame = np.full((3, h, w), 50.0, np.float32)
+if sys.argv[1] == "pinned":
+    keep = [torch.empty((3, h, w), dtype=torch.float32).pin_memory()]
+    frame = keep[0].numpy(); frame[...] = 50.0
+    planes = []
+    for (pw, ph), st in zip(L.plane_dims(w, h, 2), L.vpx_strides(w, 2)):
+        keep.append(torch.zeros((ph, st), dtype=torch.uint8).pin_memory()); planes.append(keep[-1].numpy())
+else:
+    planes = L.alloc_planes(w, h, 2)
+for _ in range(3):
+    enc.encode(frame, planes)
+print("done")
+''' % str(root)
+    env = {k: v for k, v in os.environ.items() if k != "LUMACU_QUIET"}
+    for mode, expect in (("pageable", 2), ("pinned", 0)):  # frame + plane buffer, each reported once... per context: once in total
+        r = subprocess.run([sys.executable, "-c", prog, mode], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0 and "done" in r.stdout, r.stderr[-2000:]
+        n = r.stderr.count("pageable host memory")
+        assert (n == 1) if expect else (n == 0), (mode, r.stderr[-500:])
+    quiet = subprocess.run([sys.executable, "-c", prog, "pageable"], capture_output=True, text=True, timeout=300,
+                           env=dict(env, LUMACU_QUIET="1"))
+    assert quiet.returncode == 0 and "pageable host memory" not in quiet.stderr
