@@ -188,8 +188,6 @@ enc_fn LUMA_CAT(get_encode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int walk, i
 {
     if (variant == 4)
         return prescale ? pick_enc_cfg<0, true>(sub, bytes, walk, false) : pick_enc_cfg<0, false>(sub, bytes, walk, false);
-    if (variant == kEncVariantPrefetch) /* plain kernel + L2 prefetch of the thread's next tile */
-        return prescale ? pick_enc_cfg<2, true>(sub, bytes, walk, false) : pick_enc_cfg<2, false>(sub, bytes, walk, false);
     if (variant == kEncVariantScreened) /* Lu'v' 4:2:0: screened chroma, queued redo, L2 prefetch two tiles ahead */
         return prescale ? pick_enc_cfg<6, true>(sub, bytes, walk, true) : pick_enc_cfg<6, false>(sub, bytes, walk, true);
     if (prescale)

@@ -24,6 +24,9 @@ CONFIGS = [
     ("4K PQ-12 Lu'v' 12 p3 (4:4:4)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=12, profile=3)),
     ("4K PQ-12 Lu'v' 8 p2 (wide LUT, 4:2:0)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=8, profile=2)),
     ("4K PQ-16 Lu'v' 8 p2 (-pb 16: binary search)", 3840, 2160, 8, dict(ptf="PQ", ptfBitDepth=16, colorSpace="LUV", colorBitDepth=8, profile=2)),
+    ("4K PQ-11 Lu'v' 8 p3 (4:4:4, 8-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=8, profile=3)),
+    ("4K PQ-11 Lu'v' 10 p3 (4:4:4, 10-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=10, profile=3)),
+    ("4K PQ-11 Lu'v' 10 p2 (4:2:0, 10-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=10, profile=2)),
     ("4K PQ-11 XYZ p2", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="XYZ", colorBitDepth=8, profile=2)),
     ("4K PQ-11 RGB p2", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="RGB", colorBitDepth=8, profile=2)),
     ("1080p PQ-8 Lu'v' 8 p0 (8-bit 4:2:0)", 1920, 1080, 64, dict(ptf="PQ", ptfBitDepth=8, colorSpace="LUV", colorBitDepth=8, profile=0)),

@@ -185,8 +185,8 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
     cpu_planes, _ = o.encode(rgb[0].cpu().numpy().copy(), 2, 1.0)
     for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
         assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
-    for enc_v, dec_v, cap in [(4, 4, 0), (24, 24, 0), (0, 64, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
-                              (87, 0, 0), (1067, 0, 0), (1024, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
+    for enc_v, dec_v, cap in [(4, 4, 0), (0, 24, 0), (0, 64, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
+                              (87, 0, 0), (1067, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
                               (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
         ctx.set_tuning(enc_v, dec_v, cap)
         planes = t.encode(rgb)
@@ -232,7 +232,7 @@ def _boundary_frame(w, h, seed, max_c=255.0, rel_span=2e-5):
     return np.ascontiguousarray(np.repeat(np.repeat(blocks, 2, axis=1), 2, axis=2))
 
 
-@pytest.mark.parametrize("cbits,sc", [(8, 1.0), (10, 1.0), (8, 3.5)])
+@pytest.mark.parametrize("cbits,sc", [(8, 1.0), (10, 1.0), (12, 1.0), (8, 3.5)])
 def test_screened_chroma_equals_exact_chain(lumalib, po, torch_cuda, cbits, sc):
     """The screened-chroma encode kernel (Lu'v' 4:2:0 default; luma_fast.cuh FASTC) against the exact-chain tuned kernel
     (variant 4, itself pinned against the oracle everywhere else) on 100+ Mpixel of content chosen to stress the screen:
