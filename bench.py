@@ -45,7 +45,7 @@ OTHER_CONFIGS = {
     "cfg2": dict(label="1920x1080 PQ Lu'v' 11/8-bit, profile 2", w=1920, h=1080, ptf="PQ", bits=11, cs="LUV", cbits=8,
                  frames=64, stats=False),
     "cfg3": dict(label="3840x2160 PQ 10-bit + BT.2020 YCbCr 10-bit (HDR10-equivalent), profile 2", w=3840, h=2160, ptf="PQ",
-                 bits=10, cs="YCBCR", cbits=10, frames=8, stats=False),
+                 bits=10, cs="YCBCR", cbits=10, frames=8, stats=False, also_half_float_input=True),
     "cfg4": dict(label="3840x2160 LOG 12-bit + Lu'v' 8-bit, profile 2, frame stream sharded over the ranks", w=3840, h=2160,
                  ptf="LOG", bits=12, cs="LUV", cbits=8, frames=32, min_total_frames=64, stats=False),
     "cfg5": dict(label="7680x4320 PQ Lu'v' 11/8-bit, 0.005..10000 cd/m2, per-frame sum/max/min of Y", w=7680, h=4320, ptf="PQ",
@@ -386,6 +386,30 @@ def measure_config(name: str, cfg: dict, args, local: int, rank: int, world: int
            "frac": bytes_pass / (max(enc_ms, dec_ms) / 1e3) / 1e9 / peak,
            "round_trip_frac_of_peak": 2 * bytes_pass / ((enc_ms + dec_ms) / 1e3) / 1e9 / peak,
            "search": t.quant.search_info()}
+    if cfg.get("also_half_float_input"):
+        # Informational: the same frames rounded to half-float values -- what the reference's own input path delivers
+        # (OpenEXR half pixels, src/exr_interface.cpp:73-143).  Such samples are looked up in a 65 536-entry table
+        # instead of being pushed through powf; arbitrary floats (the configuration's synthetic noise above) are not.
+        rgb_h = rgb.half().float().contiguous()
+        for _ in range(n_warm):
+            t.encode(rgb_h, planes=planes, stats=stats)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n_steps):
+            t.encode(rgb_h, planes=planes, stats=stats)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_h = e0.elapsed_time(e1) / n_steps
+        th = torch.tensor([enc_h], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        enc_h = float(th.item())
+        res["half_float_input"] = {"what": "same frames rounded to half-float (EXR-sourced content): encode reads PQ from the input table",
+                                   "encode_ms": enc_h, "encode_gbs": bytes_pass / (enc_h / 1e3) / 1e9,
+                                   "round_trip_value": world * px / ((enc_h + dec_ms) / 1e3) / 1e6}
+        t.encode(rgb, planes=planes, stats=stats)  # the planes of the configuration's own input again (parity below)
+        del rgb_h
     if stats is not None:
         st = t.stats_to_numpy(stats)
         res["stats_frame0"] = {"mean_Y": float(st["sum"][0]) / (w * h), "max_Y": float(st["max"][0]), "min_Y": float(st["min"][0])}

@@ -55,6 +55,8 @@ constexpr size_t kPqTabPqeBytes = (size_t)(0x3F8147AEu - 0x3F55C28Fu + 1u) * 4u;
 void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *pqe, float l_max);
 /* v-keyed luma search table of CS_YCBCR encode: kVdTabBytes of device memory + one flag word (non-zero = unusable) */
 constexpr size_t kVdTabBytes = (size_t)((((0x3F800000u >> 13) - (0x3D000000u >> 13) + 1u) + 3u) & ~3u) * 4u;
+/* PQ encode of every half-float bit pattern (65 536 floats) for one preScaling / Lmax */
+void launch_build_pqh(cudaStream_t st, const QuantDev &q, float *tab, float sc, int prescale, float l_max);
 void launch_build_vdtab(cudaStream_t st, const QuantDev &q, uint32_t *tab, uint32_t *bad, float l_max);
 void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
 void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);

@@ -82,6 +82,8 @@ struct EncArgs {
     /* screened-chroma kernels (luma_fast.cuh FASTC): t = screen_k * (sum of the 2x2 block's X/D resp. Y/D) + 0.5 with
      * screen_k1 = RN(maxC/4 * 4 * 410/255), screen_k2 = RN(maxC/4 * 9 * 410/255) */
     float screen_k1, screen_k2;
+    /* CS_YCBCR tuned kernels: PQenc(max(c * sc, 1e-10)) for every half-float bit pattern c (luma_pq_tables.cuh (4)); NULL = off */
+    const float *pqh;
     /* tensor-map staged kernels: CUtensorMap over the frame batch, dims {w, h, 3 planes, frames} of f32,
      * box {128, 2, 3, 1} (opaque 128 bytes so that this header does not need cuda.h) */
     alignas(64) unsigned char rgb_tmap[128];

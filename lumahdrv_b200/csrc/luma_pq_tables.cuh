@@ -16,6 +16,12 @@
  *  (2) the outer power of PQ encode, powf(b, m) with b = (c1 + c2 Lp) / (1 + c3 Lp): whatever Lp is, b lies in
  *      [c1, c2/c3] = [0.8359, 1.00878] -- 2.85 M floats.  pqe holds powf(b, m) for each of them (11.4 MB).
  *
+ *  (4) pqh: the reference's frames come from OpenEXR half-float pixels (src/exr_interface.cpp:73-143), i.e. every input
+ *      sample is one of 65 536 values.  pqh holds the complete PQ encode R' = PQenc(max(c * preScaling, 1e-10)) for every
+ *      half bit pattern (256 KB, L1/L2 resident, rebuilt when preScaling or Lmax change: one small launch).  A sample
+ *      that is a normal half-float value or zero is looked up; any other float is evaluated as before.  For
+ *      EXR-sourced content the forward path then contains no powf at all.
+ *
  * Both tables fit in the 126 MB L2 many times over; a lookup is one 32-byte sector from L2 (or L1, for neighbouring
  * pixels of natural images) instead of 110-220 instructions.  The inner power of PQ encode, Lp = powf(x / Lmax, n),
  * has an unbounded domain and stays an exact evaluation.  Every table entry is produced by powf_glibc itself, so a
@@ -23,6 +29,8 @@
  * generic kernels: per-pixel powf) against the oracle.
  */
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "luma_device.cuh"
 
@@ -125,6 +133,38 @@ __device__ __forceinline__ float pq_encode_tab(const QuantDev &q, float val, flo
     return powf_glibc(b, m);
 }
 
+/* Index of c in pqh when c is a (normal or zero) half-float value, else 0xFFFFFFFF.  Integer test on the float bits: the
+ * 13 low mantissa bits clear and the exponent in the half range -- two instructions for a sample that is not (float ->
+ * half -> float conversions would cost a quarter-rate pipe slot each, for every sample).  Half subnormals, infinities
+ * and NaN are evaluated. */
+__device__ __forceinline__ uint32_t half_index(float c)
+{
+    const uint32_t b = __float_as_uint(c);
+    if ((b & 0x1FFFu) != 0u)
+        return 0xFFFFFFFFu;
+    const uint32_t e = (b >> 23) & 0xFFu;
+    if (e - 113u <= 29u) /* 2^-14 <= |c| <= 65504 */
+        return ((b >> 16) & 0x8000u) | ((e - 112u) << 10) | ((b >> 13) & 0x3FFu);
+    return (b << 1) == 0u ? (b >> 16) : 0xFFFFFFFFu; /* +-0 */
+}
+/* PQenc of one input sample c (NOT yet multiplied by preScaling), evaluated */
+__device__ __forceinline__ float pq_encode_sample(const QuantDev &q, float c, float sc, bool prescale, float l_max)
+{
+    const float v = prescale ? __fmul_rn(c, sc) : c;
+    return pq_encode_tab(q, max_nan(v, 1e-10f), l_max);
+}
+#ifdef LUMA_PQ_TABLE_BUILDERS
+__global__ void __launch_bounds__(256) build_pqh_kernel(const QuantDev q, float *tab, float sc, int prescale, float l_max)
+{
+    powf_tables_stage();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 65536u; i += gridDim.x * blockDim.x) {
+        const float c = __half2float(__ushort_as_half((unsigned short)i));
+        const float v = prescale ? __fmul_rn(c, sc) : c;
+        tab[i] = pq_encode_tab(q, max_nan(v, 1e-10f), l_max);
+    }
+}
+#endif
+
 /* BT.2020 Y'CbCr forward / inverse of one pixel with the tables (same expressions as ycbcr_forward_px /
  * ycbcr_inverse_px in luma_device.cuh) */
 static __device__ __noinline__ float3 ycbcr_forward_px_tab(const QuantDev &q, float R, float G, float B, float l_max)
@@ -160,13 +200,23 @@ static __device__ __noinline__ float3 ycbcr_inverse_px_tab(const QuantDev &q, fl
 struct Float3x2 {
     float3 a, b;
 };
-/* LUMA_V: return v = (219 y' + 16)/255 itself in .x (the caller searches it in vdtab) instead of PQdec(v) */
-template <bool LUMA_V>
-static __device__ __noinline__ Float3x2 ycbcr_forward_px2_tab(const QuantDev &q, float3 p0, float3 p1, float l_max)
+/* Forward transform of a pixel pair.  LUMA_V: return v = (219 y' + 16)/255 itself in .x (the caller searches it in vdtab)
+ * instead of PQdec(v).  HALF: all six input samples are known to be half-float values (the caller checked its whole tile):
+ * their PQ encodes come out of pqh (preScaling folded in); otherwise they are evaluated (p0, p1 arrive WITHOUT preScaling
+ * either way). */
+template <bool LUMA_V, bool HALF>
+static __device__ __noinline__ Float3x2 ycbcr_forward_px2_tab(const QuantDev &q, const float *pqh, float3 p0, float3 p1, float sc,
+                                                                bool prescale, float l_max)
 {
-    const float Rp0 = pq_encode_tab(q, max_nan(p0.x, 1e-10f), l_max), Rp1 = pq_encode_tab(q, max_nan(p1.x, 1e-10f), l_max);
-    const float Gp0 = pq_encode_tab(q, max_nan(p0.y, 1e-10f), l_max), Gp1 = pq_encode_tab(q, max_nan(p1.y, 1e-10f), l_max);
-    const float Bp0 = pq_encode_tab(q, max_nan(p0.z, 1e-10f), l_max), Bp1 = pq_encode_tab(q, max_nan(p1.z, 1e-10f), l_max);
+    float Rp0, Gp0, Bp0, Rp1, Gp1, Bp1;
+    if (HALF) {
+        Rp0 = __ldg(pqh + half_index(p0.x)), Gp0 = __ldg(pqh + half_index(p0.y)), Bp0 = __ldg(pqh + half_index(p0.z));
+        Rp1 = __ldg(pqh + half_index(p1.x)), Gp1 = __ldg(pqh + half_index(p1.y)), Bp1 = __ldg(pqh + half_index(p1.z));
+    } else {
+        Rp0 = pq_encode_sample(q, p0.x, sc, prescale, l_max), Rp1 = pq_encode_sample(q, p1.x, sc, prescale, l_max);
+        Gp0 = pq_encode_sample(q, p0.y, sc, prescale, l_max), Gp1 = pq_encode_sample(q, p1.y, sc, prescale, l_max);
+        Bp0 = pq_encode_sample(q, p0.z, sc, prescale, l_max), Bp1 = pq_encode_sample(q, p1.z, sc, prescale, l_max);
+    }
     const float y0 = dot3(0.2627f, 0.6780f, 0.0593f, Rp0, Gp0, Bp0), y1 = dot3(0.2627f, 0.6780f, 0.0593f, Rp1, Gp1, Bp1);
     const float v0 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y0), 16.0f), 255.0f);
     const float v1 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y1), 16.0f), 255.0f);

@@ -106,6 +106,9 @@ struct lumacu_ctx {
     DeviceBuffer d_tables; /* lut | thr | bucket | ctab | dtab | ylut */
     DeviceBuffer d_pq;       /* CS_YCBCR: pqd | pqe (luma_pq_tables.cuh), built on the device for pq_lmax */
     DeviceBuffer d_vd;       /* CS_YCBCR: v-keyed luma search table + flag word, rebuilt with every quantizer */
+    DeviceBuffer d_pqh;      /* CS_YCBCR: PQ encode of every half-float input value for (pqh_sc, pqh_lmax) */
+    float pqh_sc = 0.0f, pqh_lmax = 0.0f;
+    bool pqh_valid = false;
     float pq_lmax = 0.0f;
     bool pq_valid = false, pq_off = false; /* pq_off: tests / sweeps run the tuned kernels without the tables */
     size_t tables_bytes = 0; /* bytes of d_tables in use (what lumacu_broadcast_quantizer copies to the peers) */
@@ -531,7 +534,7 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_out)
         cudaStreamSynchronize(ctx->s_out); /* an asynchronous call the caller never waited for */
-    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
+    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_pqh, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
                             &ctx->d_aux})
         if (b->p)
             cudaFree(b->p);
@@ -626,6 +629,7 @@ LUMACU_CATCH(nullptr)
 static int build_ycbcr_tables(lumacu_ctx *ctx, QuantDev &q, float max_lum)
 {
     q.pqd = nullptr, q.pqe = nullptr, q.vdtab = nullptr;
+    ctx->pqh_valid = false; /* rebuilt by the next CS_YCBCR encode launch */
     if (!ctx->pq_valid || memcmp(&ctx->pq_lmax, &max_lum, sizeof(float)) != 0) {
         ctx->pq_valid = false;
         if (reserve(ctx, ctx->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) != LUMACU_OK) {
@@ -1313,6 +1317,25 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
             smem += kEncStagedSmemBytes;
     }
     ctx->last_fast = fn != nullptr;
+    if (fn && ctx->color_space == CS_YCBCR && a.q.pqe) {
+        /* half-float input table for this launch's preScaling (EXR-sourced frames: no powf left on the forward path);
+         * built on the launch stream right before the kernel that reads it */
+        if (!ctx->pqh_valid || memcmp(&ctx->pqh_sc, &pre_scaling, 4) != 0 || memcmp(&ctx->pqh_lmax, &ctx->q.l_max, 4) != 0) {
+            ctx->pqh_valid = false;
+            if (reserve(ctx, ctx->d_pqh, 65536 * sizeof(float)) == LUMACU_OK) {
+                launch_build_pqh(st, a.q, (float *)ctx->d_pqh.p, pre_scaling, a.prescale, ctx->q.l_max);
+                CU_TRY(ctx, cudaGetLastError());
+                CU_TRY(ctx, cudaStreamSynchronize(st)); /* rare (preScaling / Lmax changed); later launches may use another stream */
+                ctx->launches++;
+                ctx->pqh_sc = pre_scaling;
+                ctx->pqh_lmax = ctx->q.l_max;
+                ctx->pqh_valid = true;
+            } else {
+                ctx->err.clear();
+            }
+        }
+        a.pqh = ctx->pqh_valid ? (const float *)ctx->d_pqh.p : nullptr;
+    }
     if (!fn)
         fn = pick_enc(ctx->color_space, sub, bytes, vec);
     const uint32_t ntiles = ((w + 3) / 4) * ((h + 1) / 2);

@@ -301,6 +301,17 @@ def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc)
     wide.reshape(-1)[rng.integers(0, wide.size, 5000)] = rng.choice(
         np.array([0.0, -1.0, np.inf, np.nan, 1e-45, 1e-38, 1e4, 1e-10, 3e38], np.float32), 5000)
     frames.append(wide)
+    # EXR-sourced content: every sample is a half-float value (looked up in the 65 536-entry input table), incl. every
+    # finite half pattern, +-0, +-inf, NaN and subnormals; and a frame that mixes such samples with arbitrary floats
+    allh = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    exr = (po.noise_frame(w, h, seed=77) / np.float32(sc)).astype(np.float16).astype(np.float32)
+    exr.reshape(-1)[: 3 * 65536] = np.tile(allh, 3)
+    frames.append(exr)
+    mixed = frames[0].copy()
+    sel = rng.random(mixed.shape) < 0.5
+    mixed[sel] = mixed[sel].astype(np.float16).astype(np.float32)
+    frames.append(mixed)
+    n = len(frames)
     rgb = torch.from_numpy(np.stack(frames)).cuda()
     ctx.set_pq_tables(False)
     ref_planes = [p.clone() for p in t.encode(rgb)]
@@ -329,9 +340,10 @@ def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc)
     assert bool(same.all()), f"decode: {(~same).sum().item()} floats differ"
     # the host libm's word on one frame of each
     o = po.Oracle().setQuantizer("PQ", 10, "YCBCR", 10, lmax, 0.01)
-    cpu_planes, _ = o.encode(frames[0].copy(), 2, sc)
-    for a, b, (pw, ph) in zip(got, cpu_planes, po.plane_dims(w, h, 2)):
-        assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
+    for f in (0, n - 2, n - 1):
+        cpu_planes, _ = o.encode(frames[f].copy(), 2, sc)
+        for a, b, (pw, ph) in zip(got, cpu_planes, po.plane_dims(w, h, 2)):
+            assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2]), f"frame {f} vs the CPU oracle"
     cpu_out = o.decode([p[1].cpu().numpy() for p in planes], w, h, 2, sc)
     assert bits_equal(out[1].cpu().numpy(), cpu_out)
 
