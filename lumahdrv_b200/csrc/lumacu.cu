@@ -7,8 +7,11 @@
  *   - derivation of the exact decision thresholds of LumaQuantizer::quantize
  *     (src/luma_quantizer.cpp:219-235) and of the bucket table that turns the
  *     reference's 11-step bisection into one table read plus <= `walk` compares;
- *   - launch configuration (persistent grid = SM count x resident blocks),
- *     staging for the host-pointer entry points, error reporting.
+ *   - the direct search tables (one or two thresholds per bucket) built from them;
+ *   - launch configuration (persistent grid = SM count x resident blocks), kernel
+ *     selection, the device-built CS_YCBCR tables;
+ *   - staging for the host-pointer entry points (banded, optionally asynchronous),
+ *     the GPU-to-GPU quantizer broadcast, error reporting.
  * There is no CPU implementation of the transform in this library: without a
  * CUDA device every compute entry point fails with LUMACU_ERR_NO_DEVICE/_CUDA.
  */
