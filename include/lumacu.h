@@ -352,13 +352,18 @@ int lumacu_last_kernel_path(const lumacu_ctx *ctx);
 /* Host-pointer entry points cut a frame into row bands whose H2D copy, kernel and D2H copy overlap on three
  * streams (DESIGN.md "host staging").  0 = automatic (about one band per 8 MiB of frame, at most 8). */
 int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
-/* Tuning sweep: pick one of the extra instantiations of the headline tuned kernels
- * (variant = 10 * PF + MINB: PF 1 = next tile prefetched into registers, MINB = resident blocks per SM
- * the register allocation is held to; 0 = the default) and optionally cap the resident blocks per SM
- * of the persistent grid (0 = whatever the occupancy calculator allows; + 100 * T sizes the blocks of a
- * multi-frame launch for T tiles per thread).  enc_variant + 1000 forces the
- * bucket + threshold luma search where the direct search table would be used.  Unknown variants fall back
- * to the default.  All variants produce identical bits. */
+/* Tuning sweep / tests: pick an instantiation of the tuned kernels instead of the default (0).  All variants produce
+ * identical bits; unknown or inapplicable ones fall back to the default family.
+ *   enc_variant   4  exact chroma chain, plain loads (the round-1 algorithm; every configuration)
+ *                67  screened chroma + queued redo + L2 prefetch two tiles ahead (any Lu'v' 4:2:0 quantizer; the default
+ *                    for 8-bit chroma)
+ *                 6, 7, 26, 27, 86, 87, 64, 84, 3, 5, 12, 13, 34, 44, 54   headline configuration only: redo policy,
+ *                    prefetch distance, tensor-map staging, occupancy and arithmetic-skipping diagnostics
+ *                    (lumahdrv_b200/csrc/luma_kern_tu.cu lists them)
+ *            + 1000  bucket + threshold luma search where a direct search table would be used
+ *   dec_variant   4  plain loads;  24  + L2 prefetch of the next tile's code words (the default);  64, 3, 5, 13-15 headline only
+ *   blocks_per_sm_cap   cap on the resident blocks per SM of the persistent grid (0 = what the occupancy calculator allows),
+ *                    + 100 * T sizes the blocks of a multi-frame launch for T tiles per thread. */
 int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap);
 
 #ifdef __cplusplus
