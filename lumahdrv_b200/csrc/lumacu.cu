@@ -1192,8 +1192,8 @@ int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint
         const uint32_t tpt = ctx->grid_tpt > 0 ? (uint32_t)ctx->grid_tpt : tpt_default;
         uint32_t coarse = (need + tpt - 1) / tpt;
         g = std::max(per_frame, std::min(coarse, resident));
-    } else if (ctx->grid_tpt > 0) { /* tuning sweep: single-frame launches sized by tiles per thread */
-        g = std::min(resident, std::max(1u, (need + (uint32_t)ctx->grid_tpt - 1) / (uint32_t)ctx->grid_tpt));
+    } else if (ctx->grid_tpt > 0) { /* tuning sweep: single-frame launches sized by tiles per thread (may exceed one wave) */
+        g = std::max(1u, (need + (uint32_t)ctx->grid_tpt - 1) / (uint32_t)ctx->grid_tpt);
     }
     *gx = std::max(1u, std::min(g, need));
     return LUMACU_OK;

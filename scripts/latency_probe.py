@@ -21,10 +21,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--enc", type=int, default=0)
+    ap.add_argument("--cap", type=int, default=0, help="lumacu_set_tuning blocks_per_sm_cap (+ 100 * tiles per thread)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     t = DeviceTransform(0)
-    t.quant.ctx.set_tuning(a.enc, 0, 0)
+    t.quant.ctx.set_tuning(a.enc, 0, a.cap)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {}
     for w, h in ((1920, 1080), (3840, 2160), (7680, 4320)):
