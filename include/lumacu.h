@@ -32,11 +32,10 @@
  *  - the host-pointer entry points accept any host memory, but only page-locked memory (lumacu_host_alloc,
  *    lumacu_host_register) moves at PCIe rate; pageable memory is staged by the driver, several times slower.  The
  *    first time a context sees a pageable frame or plane buffer it says so on stderr (LUMACU_QUIET=1 silences it).
- *  - a context is thread-compatible, not thread-safe: one host thread at a time, and ONE stream's worth of work in
- *    flight per context -- the per-frame statistics workspace and the quantizer tables belong to the context, so two
- *    launches of the same context on different caller streams must be ordered by the caller (use one context per
- *    stream / thread / GPU instead; contexts are cheap).  lumacu_set_quantizer synchronises the whole device before it
- *    replaces the tables.
+ *  - a context is thread-compatible, not thread-safe: one host thread at a time.  The "_dev" entry points may be used on
+ *    several caller streams of the same context (the statistics workspace is kept per stream; the quantizer tables are
+ *    read-only between lumacu_set_quantizer calls, which synchronise the whole device before replacing them); the
+ *    host-pointer entry points have ONE call in flight per context.
  *  - results are bit-identical to the reference CPU path for the integer
  *    planes and for the decoded floats (see DESIGN.md for the one documented
  *    libm dependency: CS_YCBCR calls powf per pixel).

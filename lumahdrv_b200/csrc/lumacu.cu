@@ -121,7 +121,12 @@ struct lumacu_ctx {
     bool fast_enc_ok = false;
 
     /* stats workspace */
-    DeviceBuffer d_partial, d_counter;
+    /* block partials + per-frame arrival counters of the statistics reduction: one pair PER STREAM the context has
+     * launched on, so that launches on different caller streams do not share them */
+    struct StatsWs {
+        DeviceBuffer partial, counter;
+    };
+    std::unordered_map<cudaStream_t, StatsWs> stats_ws;
 
     /* staging for the host-pointer entry points: row bands flow H2D (s_in) -> kernel (stream) -> D2H (s_out) */
     DeviceBuffer d_rgb, d_planes, d_stats, d_aux;
@@ -537,7 +542,11 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_out)
         cudaStreamSynchronize(ctx->s_out); /* an asynchronous call the caller never waited for */
-    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_pqh, &ctx->d_partial, &ctx->d_counter, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
+    for (auto &kv : ctx->stats_ws)
+        for (DeviceBuffer *b : {&kv.second.partial, &kv.second.counter})
+            if (b->p)
+                cudaFree(b->p);
+    for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_pqh, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
                             &ctx->d_aux})
         if (b->p)
             cudaFree(b->p);
@@ -1347,17 +1356,18 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
     if (rc)
         return rc;
     if (d_stats) {
-        rc = reserve(ctx, ctx->d_partial, (size_t)n_frames * gx * sizeof(StatsPartial));
+        lumacu_ctx::StatsWs &ws = ctx->stats_ws[st];
+        rc = reserve(ctx, ws.partial, (size_t)n_frames * gx * sizeof(StatsPartial));
         if (rc)
             return rc;
-        if ((size_t)n_frames * 4 > ctx->d_counter.cap) {
-            rc = reserve(ctx, ctx->d_counter, std::max<size_t>((size_t)n_frames * 4, 4096));
+        if ((size_t)n_frames * 4 > ws.counter.cap) {
+            rc = reserve(ctx, ws.counter, std::max<size_t>((size_t)n_frames * 4, 4096));
             if (rc)
                 return rc;
-            CU_TRY(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, ctx->d_counter.cap, st));
+            CU_TRY(ctx, cudaMemsetAsync(ws.counter.p, 0, ws.counter.cap, st));
         }
-        a.partial = (StatsPartial *)ctx->d_partial.p;
-        a.counter = (uint32_t *)ctx->d_counter.p;
+        a.partial = (StatsPartial *)ws.partial.p;
+        a.counter = (uint32_t *)ws.counter.p;
         a.stats = (FrameStatsDev *)d_stats;
     }
     fn<<<dim3(gx, n_frames), kThreads, smem, st>>>(a);

@@ -156,6 +156,40 @@ def test_bench_line_carries_parity_and_configs(torch_cuda):
     assert d["configs"]["cfg4"]["frames_total_per_step"] >= 64
 
 
+def test_one_context_on_two_streams(lumalib, po, torch_cuda):
+    """The device entry points of ONE context launched on two caller streams at once: planes, decoded floats and the
+    per-frame statistics (whose reduction workspace is kept per stream) equal the single-stream results."""
+    torch = torch_cuda
+    from lumahdrv_b200.device import DeviceTransform
+    t = DeviceTransform(0)
+    w, h, n = 1920, 1080, 6
+    rgb = [torch.from_numpy(np.stack([po.noise_frame(w, h, seed=700 + 10 * k + i) for i in range(n)])).cuda() for k in range(2)]
+    ref_planes, ref_stats = [], []
+    for k in range(2):
+        st = t.alloc_stats(n)
+        ref_planes.append([p.clone() for p in t.encode(rgb[k], stats=st)])
+        torch.cuda.synchronize()
+        ref_stats.append(t.stats_to_numpy(st).copy())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    planes = [t.alloc_planes(n, w, h) for _ in range(2)]
+    stats = [t.alloc_stats(n) for _ in range(2)]
+    outs = [torch.empty_like(rgb[0]) for _ in range(2)]
+    torch.cuda.synchronize()
+    for _ in range(20):  # interleave launches of the two streams
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                t.encode(rgb[k], planes=planes[k], stats=stats[k])
+                t.decode(planes[k], w, h, out=outs[k])
+    torch.cuda.synchronize()
+    for k in range(2):
+        for a, b in zip(planes[k], ref_planes[k]):
+            assert torch.equal(a, b), f"stream {k}: planes"
+        got = t.stats_to_numpy(stats[k])
+        assert np.array_equal(got["sum"], ref_stats[k]["sum"]) and np.array_equal(got["max"], ref_stats[k]["max"])
+        assert np.array_equal(got["min"], ref_stats[k]["min"]), f"stream {k}: statistics"
+        assert torch.equal(outs[k].view(torch.int32), t.decode(ref_planes[k], w, h).view(torch.int32))
+
+
 def test_luma_codes_are_fixed_points(lumalib, torch_cuda):
     """quantize(dequantize(code)) == code for every code of every shipped transfer function (exact property)."""
     import lumahdrv_b200 as L
