@@ -154,6 +154,8 @@ static enc_fn pick_walk(int walk)
 #endif
     if (walk == -1) /* direct search table over the thresholds' own range (both clamps on the device) */
         return encode_fast_kernel<kCS, SUB, BYTES, -1, PF, 4, PRESC, FASTC>;
+    if (walk == -4) /* direct table in global memory (very wide LUTs: 13-16 bits) */
+        return encode_fast_kernel<kCS, SUB, BYTES, -4, PF, 4, PRESC, FASTC>;
     if (walk == -3) /* 64-bit direct table, two thresholds per bucket (wide LUTs such as PQ-12) */
         return encode_fast_kernel<kCS, SUB, BYTES, -3, PF, 4, PRESC, FASTC>;
 #if LUMA_TU_CS == 2

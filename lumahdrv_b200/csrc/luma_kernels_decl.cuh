@@ -35,6 +35,7 @@ struct QuantDev {
     uint32_t d_shift, d_lo, d_n;
     uint32_t d_lo_key, d_hi_key; /* keys are clamped to [d_lo_key, d_hi_key] first (d_lo_key 0 = no lower clamp needed) */
     uint32_t d_double;           /* 1: 64-bit entries {A, B}, up to two thresholds per bucket (wide LUTs; lumacu.cu) */
+    uint32_t d_global;           /* 1: too large for shared memory (13-16 bit LUTs): the kernels read dtab from global memory */
     /* CS_YCBCR decode: code -> ((255 PQenc(lut[code])) - 16) / 219 (src/luma_quantizer.cpp:447-448), host-built with the
      * host libm: two of the eight per-pixel powf calls become a table read.  NULL for the other colour spaces. */
     const float *ylut;

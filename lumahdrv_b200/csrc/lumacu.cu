@@ -842,6 +842,46 @@ try {
         }
     }
 
+    /* Very wide LUTs (13-16 bits, e.g. `lumaenc -pb 16`, lumaenc.cpp:132): neither shared-memory table fits and the bucket
+     * walk would be too long (binary search mode).  The one-threshold-per-bucket table still exists -- it is just large
+     * (PQ-16: 2^10 floats per bucket, 0.9 MB); it stays in global memory, L1 / L2 resident, and the tuned kernels read it
+     * with one read-only load per sample (luma_fast.cuh WALK -4). */
+    uint32_t d_global = 0;
+    if (dtab.empty() && mode != SEARCH_LITERAL && max_val >= 1u && thr[0] > 0x80000000u) {
+        const uint32_t k_lo = f2u(1e-4f);
+        const uint32_t t_first = thr[0] ^ flip, t_last = thr[max_val - 1] ^ flip;
+        for (uint32_t S = 16; S >= 6 && dtab.empty(); S--) {
+            bool ok = true;
+            for (uint32_t j = 1; j < max_val && ok; j++)
+                ok = ((thr[j] ^ flip) >> S) != ((thr[j - 1] ^ flip) >> S);
+            if (!ok)
+                continue;
+            uint32_t lo = (t_first >> S) - 1u, hi = (t_last >> S) + 1u;
+            if (raw_keys)
+                lo = std::max(lo, (k_lo >> S) - 1u);
+            if (hi < lo || (size_t)(hi - lo + 1u) * 4 > ((size_t)8 << 20))
+                break;
+            const uint32_t n = hi - lo + 1u;
+            dtab.resize(n);
+            uint32_t j = 0;
+            for (uint32_t b = 0; b < n; b++) {
+                const uint32_t kb = lo + b;
+                while (j < max_val && ((thr[j] ^ flip) >> S) < kb)
+                    j++;
+                uint32_t thr_low = 1u << S;
+                if (j < max_val && ((thr[j] ^ flip) >> S) == kb)
+                    thr_low = (thr[j] ^ flip) - (kb << S);
+                dtab[b] = (j << 16) + 0x10000u - thr_low - (kb << S);
+            }
+            d_global = 1;
+            d_shift = S;
+            d_lo = lo;
+            d_lo_key = lo << S;
+            d_hi_key = ((hi + 1u) << S) - 1u;
+            dtab.resize((dtab.size() + 3) & ~(size_t)3, 0u);
+        }
+    }
+
     /* CS_YCBCR decode: per-code y' = ((255 PQenc(lut[code])) - 16) / 219 with the reference's own float expression
      * (src/luma_quantizer.cpp:447-448, 493-494) and the host libm */
     std::vector<float> ylut;
@@ -890,6 +930,7 @@ try {
     q.d_lo = d_lo;
     q.d_n = (uint32_t)dtab.size();
     q.d_double = d_double;
+    q.d_global = d_global;
     q.d_lo_key = d_lo_key;
     q.d_hi_key = d_hi_key;
     q.ylut = ylut.empty() ? nullptr : (const float *)(d + off_ylut);
@@ -921,7 +962,7 @@ try {
     if (smem_dec_fast > kMaxSmemLut)
         smem_dec_fast = 0;
     /* (the tuned search also wants every threshold to be a positive float: key > key(+0)) */
-    ctx->fast_enc_ok = (mode == SEARCH_BUCKET && smem_enc != 0 && thr[0] > 0x80000000u);
+    ctx->fast_enc_ok = (mode == SEARCH_BUCKET && smem_enc != 0 && thr[0] > 0x80000000u) || d_global != 0;
     ctx->smem_dec_fast = smem_dec_fast;
 
     if (color_space == CS_YCBCR && (rc = build_ycbcr_tables(ctx, q, max_lum)) != LUMACU_OK)
@@ -1306,8 +1347,9 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
          * which is latency-bound (PQ-12 4:2:0: 6.2 vs 5.4 TB/s), not for the exact-chain kernels, which are pipe-bound and
          * want the occupancy (PQ-12 4:4:4: 5.0 vs 5.65 TB/s with the bucket + threshold walk) */
         const bool direct = ctx->q.dtab && !ctx->no_direct && (!ctx->q.d_double || variant == kEncVariantScreened);
-        /* -1: direct table that needs the lower clamp too; -3: 64-bit entries, two thresholds per bucket */
-        const int walk_direct = ctx->q.d_double ? -3 : (ctx->q.d_lo_key ? -1 : 0);
+        /* -1: direct table that needs the lower clamp too; -3: 64-bit entries, two thresholds per bucket; -4: table in
+         * global memory */
+        const int walk_direct = ctx->q.d_global ? -4 : ctx->q.d_double ? -3 : (ctx->q.d_lo_key ? -1 : 0);
         int walk = direct ? walk_direct : (int)ctx->q.walk;
         /* CS_YCBCR without statistics: plane 0 is searched by v in the v-keyed table (-2) */
         const bool v_keyed = ctx->color_space == CS_YCBCR && a.q.vdtab && !d_stats && !ctx->no_direct && variant == kEncVariantPlain;
@@ -1324,7 +1366,7 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
             fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (fn && walk <= 0)
-            smem = walk == -2 ? kVdTabBytes : (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
+            smem = walk == -2 ? kVdTabBytes : walk == -4 ? 0 : (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
         if (fn && staged && variant != kEncVariantPlain)
             smem += kEncStagedSmemBytes;
     }
