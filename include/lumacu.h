@@ -333,7 +333,8 @@ uint64_t lumacu_launch_count(const lumacu_ctx *ctx);
 /* Describes how the luma search was configured by the last set_quantizer:
  * mode 0 = bucket table + threshold walk (shared memory), 1 = binary search
  * over the thresholds, 2 = literal replica of the reference's bisection over
- * the LUT (LUT not strictly increasing). */
+ * the LUT (LUT not strictly increasing).  This is the GENERIC kernels' search; the tuned kernels replace modes 0 and 1
+ * by direct tables where one exists (shared memory up to 12-bit LUTs, global memory for 13-16 bits). */
 int lumacu_search_info(const lumacu_ctx *ctx, int *mode, uint32_t *n_buckets, uint32_t *shift,
                        uint32_t *walk);
 

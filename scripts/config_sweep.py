@@ -23,7 +23,7 @@ CONFIGS = [
     ("cfg5 8K PQ Lu'v' 11/8 p2 (+stats)", 7680, 4320, 8, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=8, profile=2)),
     ("4K PQ-12 Lu'v' 12 p3 (4:4:4)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=12, profile=3)),
     ("4K PQ-12 Lu'v' 8 p2 (wide LUT, 4:2:0)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=12, colorSpace="LUV", colorBitDepth=8, profile=2)),
-    ("4K PQ-16 Lu'v' 8 p2 (-pb 16: binary search)", 3840, 2160, 8, dict(ptf="PQ", ptfBitDepth=16, colorSpace="LUV", colorBitDepth=8, profile=2)),
+    ("4K PQ-16 Lu'v' 8 p2 (-pb 16: global direct table)", 3840, 2160, 8, dict(ptf="PQ", ptfBitDepth=16, colorSpace="LUV", colorBitDepth=8, profile=2)),
     ("4K PQ-11 Lu'v' 8 p3 (4:4:4, 8-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=8, profile=3)),
     ("4K PQ-11 Lu'v' 10 p3 (4:4:4, 10-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=10, profile=3)),
     ("4K PQ-11 Lu'v' 10 p2 (4:2:0, 10-bit chroma)", 3840, 2160, 16, dict(ptf="PQ", ptfBitDepth=11, colorSpace="LUV", colorBitDepth=10, profile=2)),
