@@ -361,6 +361,7 @@ int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
  *                    prefetch distance, tensor-map staging, occupancy and arithmetic-skipping diagnostics
  *                    (lumahdrv_b200/csrc/luma_kern_tu.cu lists them)
  *            + 1000  bucket + threshold luma search where a direct search table would be used
+ *            + 2000  the (32-bit-entry) direct search table read from global memory instead of staged into shared memory
  *   dec_variant   4  plain loads;  24  + L2 prefetch of the next tile's code words (the default);  64, 3, 5, 13-15 headline only
  *   blocks_per_sm_cap   cap on the resident blocks per SM of the persistent grid (0 = what the occupancy calculator allows),
  *                    + 100 * T sizes the blocks of a multi-frame launch for T tiles per thread. */

@@ -100,6 +100,7 @@ struct lumacu_ctx {
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
     int grid_tpt = 0;                     /* tuning sweep: tiles per thread of a multi-frame launch (0 = default) */
     bool no_direct = false;               /* tuning sweep / tests: bucket + threshold search even when the direct table exists */
+    bool global_direct = false;           /* tuning sweep / tests: read the (32-bit) direct table from global memory, no staging */
 
     /* quantizer */
     bool configured = false;
@@ -1119,7 +1120,8 @@ try {
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (enc_variant < 0 || dec_variant < 0 || blocks_per_sm_cap < 0)
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_set_tuning: negative argument");
-    ctx->no_direct = enc_variant >= 1000; /* 1000 + variant: bucket + threshold search instead of the direct table */
+    ctx->no_direct = enc_variant >= 1000 && enc_variant < 2000; /* 1000 + variant: bucket + threshold search instead of the direct table */
+    ctx->global_direct = enc_variant >= 2000;                   /* 2000 + variant: direct table read from global memory (no staging) */
     ctx->enc_variant = enc_variant % 1000;
     ctx->dec_variant = dec_variant;
     ctx->grid_cap = blocks_per_sm_cap % 100;     /* blocks_per_sm_cap = cap + 100 * tiles_per_thread */
@@ -1349,7 +1351,7 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
         const bool direct = ctx->q.dtab && !ctx->no_direct && (!ctx->q.d_double || variant == kEncVariantScreened);
         /* -1: direct table that needs the lower clamp too; -3: 64-bit entries, two thresholds per bucket; -4: table in
          * global memory */
-        const int walk_direct = ctx->q.d_global ? -4 : ctx->q.d_double ? -3 : (ctx->q.d_lo_key ? -1 : 0);
+        const int walk_direct = (ctx->q.d_global || (ctx->global_direct && !ctx->q.d_double)) ? -4 : ctx->q.d_double ? -3 : (ctx->q.d_lo_key ? -1 : 0);
         int walk = direct ? walk_direct : (int)ctx->q.walk;
         /* CS_YCBCR without statistics: plane 0 is searched by v in the v-keyed table (-2) */
         const bool v_keyed = ctx->color_space == CS_YCBCR && a.q.vdtab && !d_stats && !ctx->no_direct && variant == kEncVariantPlain;

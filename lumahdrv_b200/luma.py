@@ -104,7 +104,7 @@ class Context:
 
     def set_tuning(self, enc_variant: int = 0, dec_variant: int = 0, blocks_per_sm_cap: int = 0) -> None:
         """lumacu_set_tuning: pick an instantiation of the tuned kernels (0 = default; 1000 + v = bucket/threshold
-        luma search instead of the direct table).  Every variant produces identical bits."""
+        luma search instead of the direct table, 2000 + v = direct table read from global memory).  Every variant produces identical bits."""
         check(self._lib.lumacu_set_tuning(self.handle, int(enc_variant), int(dec_variant), int(blocks_per_sm_cap)),
               self.handle, "lumacu_set_tuning")
 

@@ -220,7 +220,7 @@ def test_every_tuning_variant_produces_identical_bits(lumalib, po, torch_cuda, w
     for a, b, (pw, ph) in zip(ref_planes, cpu_planes, po.plane_dims(w, h, 2)):
         assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
     for enc_v, dec_v, cap in [(4, 4, 0), (0, 24, 0), (0, 64, 0), (27, 0, 0), (6, 0, 0), (7, 0, 0), (26, 0, 0), (67, 0, 0), (64, 0, 0), (86, 0, 0),
-                              (87, 0, 0), (1067, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0),
+                              (87, 0, 0), (1067, 0, 0), (1004, 0, 0), (3, 3, 0), (5, 5, 0), (84, 13, 0), (1004, 14, 0), (1003, 15, 0), (1012, 0, 0), (1013, 0, 0), (2067, 0, 0), (2004, 0, 0), (2067, 0, 400),
                               (0, 0, 2), (0, 0, 3200), (0, 0, 101)]:
         ctx.set_tuning(enc_v, dec_v, cap)
         planes = t.encode(rgb)
