@@ -29,6 +29,7 @@ LUMA_DECL_GENERIC(3)
  * configuration in a few more for the tuning sweep.
  * Return NULL when there is no instantiation for the request. */
 constexpr int kEncVariantPlain = 4, kDecVariantPlain = 4;
+constexpr int kDecVariantGlobalLut = 1024; /* decode: luma LUT stays in global memory (luma_fast.cuh PF bit 4) */
 constexpr int kDecVariantPrefetch = 24; /* decode: plain loads + L2 prefetch of the next tile (luma_fast.cuh PF 2) */
 constexpr int kEncVariantScreened = 67; /* Lu'v' 4:2:0: screened chroma, queued redo, L2 prefetch two tiles ahead (luma_fast.cuh FASTC 2, PF 6) */
 constexpr unsigned kEncStagedSmemBytes = 6u * 512u * 8u; /* luma_fast.cuh kEncStageBlock */

@@ -246,6 +246,8 @@ dec_fn LUMA_CAT(get_decode_fast_cs, LUMA_TU_CS)(bool sub, int bytes, int variant
             return bytes == 2 ? decode_fast_kernel<kCS, true, 2, 2, 4> : decode_fast_kernel<kCS, true, 1, 2, 4>;
         return bytes == 2 ? decode_fast_kernel<kCS, false, 2, 2, 4> : decode_fast_kernel<kCS, false, 1, 2, 4>;
     }
+    if (variant == kDecVariantGlobalLut && bytes == 2) /* 14-16-bit LUTs: luma LUT read in place, + L2 prefetch */
+        return sub ? decode_fast_kernel<kCS, true, 2, 18, 4> : decode_fast_kernel<kCS, false, 2, 18, 4>;
 #if LUMA_TU_CS == 0
     if (sub && bytes == 2) {
         switch (variant) {

@@ -119,6 +119,8 @@ struct lumacu_ctx {
     float max_lum = 0.0f;
     size_t smem_enc = 0, smem_dec = 0;
     size_t smem_dec_fast = 0; /* lut + chroma table; 0 = fast decode unavailable */
+    bool dec_global_lut = false; /* tuned decode with the luma LUT in global memory, chroma table (smem_dec_ctab bytes) in shared */
+    size_t smem_dec_ctab = 0;
     bool fast_enc_ok = false;
 
     /* stats workspace */
@@ -965,6 +967,9 @@ try {
     /* (the tuned search also wants every threshold to be a positive float: key > key(+0)) */
     ctx->fast_enc_ok = (mode == SEARCH_BUCKET && smem_enc != 0 && thr[0] > 0x80000000u) || d_global != 0;
     ctx->smem_dec_fast = smem_dec_fast;
+    /* LUT too large for shared memory (14-16 bits) but the chroma table fits: tuned decode with the LUT read in place */
+    ctx->dec_global_lut = smem_dec_fast == 0 && ctab.size() * 4 <= kMaxSmemLut;
+    ctx->smem_dec_ctab = ctab.size() * 4;
 
     if (color_space == CS_YCBCR && (rc = build_ycbcr_tables(ctx, q, max_lum)) != LUMACU_OK)
         return rc;
@@ -1038,6 +1043,8 @@ try {
         dst->smem_enc = src->smem_enc;
         dst->smem_dec = src->smem_dec;
         dst->smem_dec_fast = src->smem_dec_fast;
+        dst->dec_global_lut = src->dec_global_lut;
+        dst->smem_dec_ctab = src->smem_dec_ctab;
         dst->fast_enc_ok = src->fast_enc_ok;
         dst->configured = true;
     }
@@ -1357,15 +1364,17 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
         const bool v_keyed = ctx->color_space == CS_YCBCR && a.q.vdtab && !d_stats && !ctx->no_direct && variant == kEncVariantPlain;
         if (v_keyed)
             walk = -2;
-        fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
-        if (!fn && direct) { /* tuning variants exist for one search flavour only */
+        /* the bucket + threshold walk needs its tables in shared memory (fast_enc_ok may rest on the global table alone) */
+        const bool walk_ok = ctx->q.search_mode == SEARCH_BUCKET && ctx->smem_enc != 0;
+        fn = (walk > 0 && !walk_ok) ? nullptr : pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
+        if (!fn && direct && walk_ok) { /* tuning variants exist for one search flavour only */
             walk = (int)ctx->q.walk;
             fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (!fn && variant != kEncVariantPlain) { /* e.g. no screened instantiation for this search flavour */
             variant = kEncVariantPlain;
             walk = direct ? walk_direct : (int)ctx->q.walk;
-            fn = pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
+            fn = (walk > 0 && !walk_ok) ? nullptr : pick_enc_fast(ctx->color_space, sub, bytes, walk, variant, a.prescale != 0);
         }
         if (fn && walk <= 0)
             smem = walk == -2 ? kVdTabBytes : walk == -4 ? 0 : (size_t)ctx->q.d_n * 4; /* d_n is a multiple of 4 entries */
@@ -1514,6 +1523,9 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
         if (!fn)
             fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
         smem = ctx->smem_dec_fast;
+    } else if (vec && small32 && ctx->dec_global_lut && bytes == 2 && !ctx->force_generic && !opt.passthrough && !opt.display) {
+        fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantGlobalLut);
+        smem = ctx->smem_dec_ctab;
     }
     ctx->last_fast = fn != nullptr;
     if (!fn)

@@ -317,6 +317,59 @@ def test_screened_chroma_equals_exact_chain(lumalib, po, torch_cuda, cbits, sc):
             assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
 
 
+@pytest.mark.parametrize("bits,cbits,profile", [(12, 8, 2), (12, 12, 3), (13, 8, 2), (14, 10, 3), (16, 8, 2), (16, 16, 3)])
+def test_wide_luts_run_the_tuned_table_kernels(lumalib, po, torch_cuda, bits, cbits, profile):
+    """12-bit LUTs search a 64-bit two-threshold table in shared memory (screened kernel) or the bucket walk; 13-16-bit
+    LUTs (`lumaenc -pb 16`) a one-threshold direct table that stays in global memory (luma_fast.cuh WALK -3 / -4).
+    Every LUT entry, every midpoint between neighbours and the floats either side of both are in the frames; planes
+    equal the generic kernel's (binary search over the thresholds) and the CPU oracle's, and the tuned kernel ran."""
+    import torch
+    from lumahdrv_b200.device import DeviceTransform
+
+    w, h = 1024, 512
+    t = DeviceTransform(0, ptf="PQ", ptfBitDepth=bits, colorSpace="LUV", colorBitDepth=cbits, profile=profile)
+    ctx = t.quant.ctx
+    lut = t.quant.getMapping().astype(np.float32)
+    rng = np.random.default_rng(bits * 100 + cbits)
+    mid = (0.5 * (lut[:-1].astype(np.float64) + lut[1:])).astype(np.float32)
+    edge = np.concatenate([lut, mid, np.nextafter(mid, np.float32(0)), np.nextafter(mid, np.float32(np.inf)),
+                           np.nextafter(lut, np.float32(0)), np.nextafter(lut, np.float32(np.inf))]).astype(np.float32)
+    frames = []
+    for i in range(3):
+        f = po.noise_frame(w, h, seed=900 + bits + i)
+        flat = f.reshape(3, -1)
+        # grey pixels (R = G = B = L gives Y within an ulp or two of L) plus pixels whose Y is near a decision point
+        pick = rng.permutation(edge)[: flat.shape[1] // 2]
+        pos = rng.choice(flat.shape[1], size=pick.size, replace=False)
+        flat[:, pos] = pick[None, :]
+        frames.append(f)
+    rgb = torch.from_numpy(np.stack(frames)).cuda()
+    ctx.set_kernel_path(1)
+    generic = [p.clone() for p in t.encode(rgb)]
+    assert ctx.last_kernel_path == 0
+    ctx.set_kernel_path(0)
+    for tune in (0, 4, 67, 1004):
+        ctx.set_tuning(tune)
+        got = t.encode(rgb)
+        # 1000 + v asks for the bucket + threshold walk, which the tuned kernels do not have for LUTs this dense
+        tuned = 0 if (tune >= 1000 and bits >= 13) else 1
+        assert ctx.last_kernel_path == tuned, f"tuning {tune}: kernel path {ctx.last_kernel_path}"
+        for p, (a, b) in enumerate(zip(got, generic)):
+            assert torch.equal(a, b), f"tuning {tune}: plane {p} differs in {(a != b).sum().item()} bytes"
+    ctx.set_tuning(0)
+    o = po.Oracle().setQuantizer("PQ", bits, "LUV", cbits)
+    cpu_planes, _ = o.encode(frames[0].copy(), profile, 1.0)
+    for a, b, (pw, ph) in zip(generic, cpu_planes, po.plane_dims(w, h, profile)):
+        assert np.array_equal(a[0].cpu().numpy()[:ph, :pw * 2], b[:ph, :pw * 2])
+    out_tuned = t.decode(generic, w, h).clone()
+    # 14-16-bit LUTs do not fit in shared memory: the tuned decode kernel reads them in place (chroma table permitting)
+    assert ctx.last_kernel_path == (1 if cbits <= 14 else 0)
+    ctx.set_kernel_path(1)
+    out_generic = t.decode(generic, w, h)
+    ctx.set_kernel_path(0)
+    assert torch.equal(out_tuned.view(torch.int32), out_generic.view(torch.int32))
+
+
 @pytest.mark.parametrize("lmax,sc", [(1e4, 1.0), (1000.0, 20.0)])
 def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc):
     """CS_YCBCR tuned kernels read PQ decode and the outer power of PQ encode from exhaustive device-built tables
