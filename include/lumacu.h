@@ -315,6 +315,12 @@ int lumacu_test_frame_dev(lumacu_ctx *ctx, float *d_rgb, uint32_t w, uint32_t h,
  * reference ("luminance only frames not yet supported"). */
 int lumacu_half_rgba_to_frame_dev(lumacu_ctx *ctx, const void *d_rgba_half, uint32_t w, uint32_t h, int channels,
                                   float *d_rgb, void *stream);
+/* The pixel loop of ExrInterface::writeFrame (src/exr_interface.cpp:157-187), the sink lumadec writes decoded frames
+ * to: planar f32 frame -> interleaved half-float RGBA pixels (8 bytes each, alpha 0).  float -> half as Imf's half(float)
+ * does it: round to nearest even, overflow to infinity, NaN keeps sign and top payload bits.  OpenEXR is not part of the
+ * reference tree ("parity unpinned" against it; the test compares with numpy's float16 cast, the same function). */
+int lumacu_frame_to_half_rgba_dev(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_t h, void *d_rgba_half,
+                                  void *stream);
 
 /* PfsInterface::readFrame / writeFrame (src/pfs_interface.cpp:57-113, :115-152) minus the stream parsing: a PFS frame
  * carries X, Y, Z as three separate w*h float arrays; the reference runs pfstools' pfs::transformColorSpace

@@ -101,6 +101,7 @@ SIGNATURES = {
                                      C.c_int32, C.c_uint32, _P, C.c_size_t, _P]),
     "lumacu_test_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P]),
     "lumacu_half_rgba_to_frame_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
+    "lumacu_frame_to_half_rgba_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "lumacu_pfs_xyz_to_frame_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "lumacu_frame_to_pfs_xyz_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "lumacu_set_host_bands": (C.c_int, [_P, C.c_int]),

@@ -117,6 +117,10 @@ void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgb
 {
     half_rgba_to_frame_kernel<<<blocks, kThreads, 0, st>>>((const uint2 *)rgba, rgb, n, mode);
 }
+void launch_frame_to_half_rgba(unsigned blocks, cudaStream_t st, const float *rgb, void *rgba, size_t n)
+{
+    frame_to_half_rgba_kernel<<<blocks, kThreads, 0, st>>>(rgb, (uint2 *)rgba, n);
+}
 
 void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,
                          float *o0, float *o1, float *o2, size_t n)

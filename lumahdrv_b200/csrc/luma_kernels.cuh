@@ -692,6 +692,30 @@ __global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint
     }
 }
 
+/* ExrInterface::writeFrame's pixel loop (src/exr_interface.cpp:157-187): planar f32 frame -> interleaved Imf::Rgba
+ * pixels, p.r = float (Imf's half(float): round to nearest even, overflow to infinity, a NaN keeps its sign and its top
+ * ten payload bits with the lowest forced to 1 if they are all zero -- OpenEXR is not part of the reference tree, "parity
+ * unpinned"; numpy's float32 -> float16 cast is the same function and is what the test compares with), p.a = 0. */
+__device__ __forceinline__ uint32_t float_to_half_bits(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) { /* NaN */
+        const uint32_t m = (u & 0x007fffffu) >> 13;
+        return ((u >> 16) & 0x8000u) | 0x7c00u | m | (m == 0u ? 1u : 0u);
+    }
+    return (uint32_t)__half_as_ushort(__float2half_rn(f));
+}
+__global__ void __launch_bounds__(kThreads) frame_to_half_rgba_kernel(const float *__restrict__ rgb, uint2 *__restrict__ rgba, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float r = __ldcs(rgb + i), g = __ldcs(rgb + n + i), b = __ldcs(rgb + 2 * n + i);
+        uint2 v;
+        v.x = float_to_half_bits(r) | (float_to_half_bits(g) << 16);
+        v.y = float_to_half_bits(b); /* alpha = half(0) */
+        __stcs(rgba + i, v);
+    }
+}
+
 /* PfsInterface::readFrame / writeFrame (src/pfs_interface.cpp:57-113, :115-152): a PFS stream carries the colour
  * channels X, Y, Z as three separate float arrays; the reference converts them with pfstools'
  * pfs::transformColorSpace(CS_XYZ -> CS_RGB) (:84) -- resp. CS_RGB -> CS_XYZ (:140) -- and memcpy's the three channels

@@ -1618,6 +1618,26 @@ try {
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
+extern "C" int lumacu_frame_to_half_rgba_dev(lumacu_ctx *ctx, const float *d_rgb, uint32_t w, uint32_t h, void *d_rgba_half,
+                                             void *stream)
+try {
+    if (!ctx)
+        return LUMACU_ERR_INVALID_ARGUMENT;
+    if (!d_rgba_half || !d_rgb || !w || !h)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_frame_to_half_rgba_dev: NULL pointer or empty size");
+    if (!aligned(d_rgba_half, 8))
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_frame_to_half_rgba_dev: pixels must be 8-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t n = (size_t)w * h;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    launch_frame_to_half_rgba(blocks, st, d_rgb, d_rgba_half, n);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return LUMACU_OK;
+}
+LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
 /* PFS frame source / sink (src/pfs_interface.cpp:57-113, :115-152): three separate channel arrays <-> planar frame */
 static int pfs_channels(lumacu_ctx *ctx, bool to_rgb, const float *a0, const float *a1, const float *a2, float *o0, float *o1,
                         float *o2, uint32_t w, uint32_t h, void *stream, const char *who)

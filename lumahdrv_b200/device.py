@@ -119,6 +119,18 @@ class DeviceTransform:
                                                       _stream_ptr(self.device)), hnd, "lumacu_half_rgba_to_frame_dev")
         return out
 
+    def frame_to_half_rgba(self, rgb: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[3, h, w] f32 -> [h, w, 4] float16 (Imf::Rgba pixels, alpha 0), like ExrInterface::writeFrame's pixel loop."""
+        if rgb.dtype != torch.float32 or rgb.dim() != 3 or rgb.shape[0] != 3 or not rgb.is_contiguous() or not rgb.is_cuda:
+            raise LumaException("rgb must be a contiguous CUDA float32 [3, h, w] tensor", 1)
+        _, h, w = rgb.shape
+        if out is None:
+            out = torch.empty((h, w, 4), dtype=torch.float16, device=self.device)
+        hnd = self.quant.ctx.handle
+        check(self._lib.lumacu_frame_to_half_rgba_dev(hnd, rgb.data_ptr(), w, h, out.data_ptr(), _stream_ptr(self.device)),
+              hnd, "lumacu_frame_to_half_rgba_dev")
+        return out
+
     def pfs_xyz_to_frame(self, x: torch.Tensor, y: torch.Tensor, z: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """PfsInterface::readFrame's colour step (src/pfs_interface.cpp:80-102): the X, Y, Z channel arrays of a PFS
         frame ([h, w] f32 each) -> planar RGB frame [3, h, w]."""

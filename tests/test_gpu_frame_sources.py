@@ -55,6 +55,38 @@ def test_half_rgba_to_frame(dt, channels):
     assert np.array_equal(got.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])
 
 
+def test_frame_to_half_rgba(dt):
+    """ExrInterface::writeFrame's pixel loop (src/exr_interface.cpp:167-175): p.r/g/b = float -> half, p.a = 0.  Imf's
+    half(float) rounds to nearest even, overflows to infinity and keeps a NaN's sign and top payload bits; numpy's
+    float32 -> float16 cast is the same function (OpenEXR is not in the reference tree: parity unpinned against it)."""
+    import torch
+    h, w = 257, 510
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 1 << 32, size=(3, h, w), dtype=np.uint64).astype(np.uint32)  # any float: NaNs, infs, subnormals
+    f = bits.view(np.float32).copy()
+    flat = f.reshape(-1)
+    # the half range densely: ties (exactly between two halfs), the overflow threshold 65520, half subnormals, signed zeros
+    allh = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    fin = allh[np.isfinite(allh)]
+    nxt = np.nextafter(fin.astype(np.float16), np.float16(np.inf)).astype(np.float32)
+    ties = ((fin.astype(np.float64) + nxt.astype(np.float64)) / 2).astype(np.float32)
+    special = np.concatenate([allh, ties, np.nextafter(ties, np.float32(0)), np.nextafter(ties, np.float32(np.inf)),
+                              np.array([65504.0, 65519.99, 65520.0, 65536.0, 1e30, -65520.0, 2.0 ** -25, 2.0 ** -24, 1.5 * 2.0 ** -25,
+                                        0.0, -0.0, np.inf, -np.inf], np.float32),
+                              np.array([0x7f800001, 0xff800001, 0x7fc00000, 0xffc12345, 0x7f801fff, 0x7f802000], np.uint32).view(np.float32)])
+    flat[: special.size] = special
+    got = dt.frame_to_half_rgba(torch.from_numpy(f).cuda()).cpu().numpy().view(np.uint16)
+    with np.errstate(over="ignore", invalid="ignore"):
+        ref = np.stack([f[0], f[1], f[2], np.zeros_like(f[0])], axis=-1).astype(np.float16).view(np.uint16)
+    assert got.shape == (h, w, 4)
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} half words differ"
+    # read back through the source kernel: half -> float is exact, so the round trip is the half-rounded frame
+    back = dt.half_rgba_to_frame(torch.from_numpy(got.view(np.float16)).cuda(), 7).cpu().numpy()
+    want = ref[..., :3].view(np.float16).astype(np.float32).transpose(2, 0, 1)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(back), nan) and np.array_equal(back.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+
+
 def test_half_rgba_rejects_luminance_only(dt, lumalib):
     import torch
     with pytest.raises(lumalib.LumaException, match="luminance only"):
