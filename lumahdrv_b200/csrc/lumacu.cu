@@ -1862,6 +1862,24 @@ static void note_if_pageable(lumacu_ctx *ctx, const void *p, const char *what)
                     "lumacu_host_alloc or page-lock it with lumacu_host_register. (LUMACU_QUIET=1 silences this note.)\n", what);
 }
 
+/* A host-pointer call that fails half way (some bands already queued) must not return while copies into or out of the
+ * caller's buffers are still in flight: drain the three streams unless the call got as far as handing over to
+ * finish_pending. */
+struct DrainUnlessQueued {
+    lumacu_ctx *ctx;
+    bool queued = false;
+    explicit DrainUnlessQueued(lumacu_ctx *c) : ctx(c) {}
+    ~DrainUnlessQueued()
+    {
+        if (queued)
+            return;
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_out);
+        cudaGetLastError();
+    }
+};
+
 static int ensure_async_state(lumacu_ctx *ctx)
 {
     if (!ctx->h_pin) {
@@ -1913,6 +1931,7 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
     LaunchOpts opt;
     opt.passthrough = passthrough;
     opt.rgb_plane_stride = npx; /* a band's planes are still a whole frame apart */
+    DrainUnlessQueued drain(ctx);
     for (int b = 0; b < nb; b++) {
         const uint32_t y0 = band_row(h, nb, b), y1 = band_row(h, nb, b + 1), rows = y1 - y0;
         /* the band's rows of the three planes in one strided copy (pitch = one plane) */
@@ -1944,6 +1963,7 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
         CU_TRY(ctx, cudaMemcpyAsync(ctx->h_pin, d_stats, sizeof(lumacu_frame_stats) * nb, cudaMemcpyDeviceToHost, ctx->s_out));
     if (write_back) /* with the in-place side effect the caller's frame is busy until the last D2H copy */
         CU_TRY(ctx, cudaEventRecord(ctx->ev_input, ctx->s_out));
+    drain.queued = true;
     ctx->pending = true;
     ctx->pending_stats = stats;
     ctx->pending_bands = nb;
@@ -1996,6 +2016,7 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
     LaunchOpts opt;
     opt.passthrough = passthrough;
     opt.rgb_plane_stride = npx;
+    DrainUnlessQueued drain(ctx);
     for (int b = 0; b < nb; b++) {
         const uint32_t y0 = nb == 1 ? 0 : band_row(h, nb, b), y1 = nb == 1 ? h : band_row(h, nb, b + 1), rows = y1 - y0;
         const uint8_t *bp[3];
@@ -2018,6 +2039,7 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
         CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3, cudaMemcpyDeviceToHost,
                                       ctx->s_out));
     }
+    drain.queued = true;
     ctx->pending = true;
     ctx->pending_stats = nullptr;
     ctx->pending_bands = nb;
