@@ -68,7 +68,8 @@ def test_frame_to_half_rgba(dt):
     # the half range densely: ties (exactly between two halfs), the overflow threshold 65520, half subnormals, signed zeros
     allh = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
     fin = allh[np.isfinite(allh)]
-    nxt = np.nextafter(fin.astype(np.float16), np.float16(np.inf)).astype(np.float32)
+    with np.errstate(over="ignore"):  # the neighbour above the largest finite half is infinity
+        nxt = np.nextafter(fin.astype(np.float16), np.float16(np.inf)).astype(np.float32)
     ties = ((fin.astype(np.float64) + nxt.astype(np.float64)) / 2).astype(np.float32)
     special = np.concatenate([allh, ties, np.nextafter(ties, np.float32(0)), np.nextafter(ties, np.float32(np.inf)),
                               np.array([65504.0, 65519.99, 65520.0, 65536.0, 1e30, -65520.0, 2.0 ** -25, 2.0 ** -24, 1.5 * 2.0 ** -25,
