@@ -210,6 +210,20 @@ int lumacu_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profi
 int lumacu_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3],
                   uint32_t w, uint32_t h, int profile, float pre_scaling, float *rgb);
 
+/* EXR at either end without the f32 detour over PCIe.  The reference's drivers read their frames from OpenEXR files as
+ * half-float Imf::Rgba pixels (ExrInterface::readFrame, src/exr_interface.cpp:73-143; lumaenc.cpp) and lumadec writes them
+ * back the same way (ExrInterface::writeFrame, :157-187); between the file and LumaEncoder::encode / after
+ * LumaDecoder::decode the CPU expands / rounds every pixel.  These two calls take / deliver the half pixels themselves
+ * (w*h*8 bytes, host memory): the bus carries 8 B/px instead of 12 and the pixel loops run on the device, band by band
+ * inside the same three-stream pipeline.  Results are those of the reference's own sequence: planes identical to
+ * readFrame's loop followed by lumacu_encode (channels = Imf::RgbaChannels as for lumacu_half_rgba_to_frame_dev);
+ * pixels identical to lumacu_decode followed by writeFrame's loop (lumacu_frame_to_half_rgba_dev). */
+int lumacu_encode_half_rgba(lumacu_ctx *ctx, const void *rgba_half, uint32_t w, uint32_t h, int channels, int profile,
+                            float pre_scaling, uint8_t *const planes[3], const int32_t strides[3],
+                            lumacu_frame_stats *stats);
+int lumacu_decode_half_rgba(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                            uint32_t h, int profile, float pre_scaling, void *rgba_half);
+
 /* Asynchronous forms of the two calls above: the copies and the kernel are queued on the context's streams and the
  * call returns at once, so that the host thread can do something else meanwhile -- run libvpx on the previous
  * frame's planes (what LumaEncoder::run does between two encode() calls, include/luma/luma_encoder.h:142-148), or

@@ -90,6 +90,9 @@ SIGNATURES = {
     "lumacu_encode_async": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _PP3, _PI3, C.c_int,
                                       C.POINTER(FrameStats)]),
     "lumacu_decode_async": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
+    "lumacu_encode_half_rgba": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, _PP3, _PI3,
+                                          C.POINTER(FrameStats)]),
+    "lumacu_decode_half_rgba": (C.c_int, [_P, _PP3, _PI3, C.c_uint32, C.c_uint32, C.c_int, C.c_float, _P]),
     "lumacu_wait_input": (C.c_int, [_P]),
     "lumacu_wait": (C.c_int, [_P]),
     "lumacu_pending": (C.c_int, [_P]),

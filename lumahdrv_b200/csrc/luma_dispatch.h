@@ -60,8 +60,8 @@ constexpr size_t kVdTabBytes = (size_t)((((0x3F800000u >> 13) - (0x3D000000u >> 
 void launch_build_pqh(cudaStream_t st, const QuantDev &q, float *tab, float sc, int prescale, float l_max);
 void launch_build_vdtab(cudaStream_t st, const QuantDev &q, uint32_t *tab, uint32_t *bad, float l_max);
 void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w, uint32_t h);
-void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode);
-void launch_frame_to_half_rgba(unsigned blocks, cudaStream_t st, const float *rgb, void *rgba, size_t n);
+void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, size_t plane_stride, int mode);
+void launch_frame_to_half_rgba(unsigned blocks, cudaStream_t st, const float *rgb, void *rgba, size_t n, size_t plane_stride);
 void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,
                          float *o0, float *o1, float *o2, size_t n);
 void launch_display_linear(unsigned blocks, unsigned n_frames, cudaStream_t st, const DecArgs &a, int cs, int sub, int bytes);

@@ -113,13 +113,13 @@ void launch_test_frame(unsigned blocks, cudaStream_t st, float *rgb, uint32_t w,
     test_frame_kernel<<<blocks, kThreads, 0, st>>>(rgb, w, h);
 }
 
-void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, int mode)
+void launch_half_rgba_to_frame(unsigned blocks, cudaStream_t st, const void *rgba, float *rgb, size_t n, size_t plane_stride, int mode)
 {
-    half_rgba_to_frame_kernel<<<blocks, kThreads, 0, st>>>((const uint2 *)rgba, rgb, n, mode);
+    half_rgba_to_frame_kernel<<<blocks, kThreads, 0, st>>>((const uint2 *)rgba, rgb, n, plane_stride, mode);
 }
-void launch_frame_to_half_rgba(unsigned blocks, cudaStream_t st, const float *rgb, void *rgba, size_t n)
+void launch_frame_to_half_rgba(unsigned blocks, cudaStream_t st, const float *rgb, void *rgba, size_t n, size_t plane_stride)
 {
-    frame_to_half_rgba_kernel<<<blocks, kThreads, 0, st>>>(rgb, (uint2 *)rgba, n);
+    frame_to_half_rgba_kernel<<<blocks, kThreads, 0, st>>>(rgb, (uint2 *)rgba, n, plane_stride);
 }
 
 void launch_pfs_channels(bool to_rgb, unsigned blocks, cudaStream_t st, const float *a0, const float *a1, const float *a2,

@@ -675,7 +675,7 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h16)
 {
     return __half2float(__ushort_as_half((unsigned short)h16));
 }
-__global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint2 *rgba, float *rgb, size_t n, int mode)
+__global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint2 *rgba, float *rgb, size_t n, size_t plane_stride, int mode)
 {
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
         const uint2 v = __ldcs(rgba + i);
@@ -687,8 +687,8 @@ __global__ void __launch_bounds__(kThreads) half_rgba_to_frame_kernel(const uint
         else if (mode == 4)
             r = g = b;
         __stcs(rgb + i, r);
-        __stcs(rgb + n + i, g);
-        __stcs(rgb + 2 * n + i, b);
+        __stcs(rgb + plane_stride + i, g);
+        __stcs(rgb + 2 * plane_stride + i, b);
     }
 }
 
@@ -705,10 +705,11 @@ __device__ __forceinline__ uint32_t float_to_half_bits(float f)
     }
     return (uint32_t)__half_as_ushort(__float2half_rn(f));
 }
-__global__ void __launch_bounds__(kThreads) frame_to_half_rgba_kernel(const float *__restrict__ rgb, uint2 *__restrict__ rgba, size_t n)
+__global__ void __launch_bounds__(kThreads) frame_to_half_rgba_kernel(const float *__restrict__ rgb, uint2 *__restrict__ rgba, size_t n,
+                                                                      size_t plane_stride)
 {
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
-        const float r = __ldcs(rgb + i), g = __ldcs(rgb + n + i), b = __ldcs(rgb + 2 * n + i);
+        const float r = __ldcs(rgb + i), g = __ldcs(rgb + plane_stride + i), b = __ldcs(rgb + 2 * plane_stride + i);
         uint2 v;
         v.x = float_to_half_bits(r) | (float_to_half_bits(g) << 16);
         v.y = float_to_half_bits(b); /* alpha = half(0) */

@@ -133,6 +133,7 @@ struct lumacu_ctx {
 
     /* staging for the host-pointer entry points: row bands flow H2D (s_in) -> kernel (stream) -> D2H (s_out) */
     DeviceBuffer d_rgb, d_planes, d_stats, d_aux;
+    DeviceBuffer d_half; /* interleaved half RGBA staging of the *_half_rgba host entry points (8 B/px) */
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
     int host_bands = 0;               /* tuning: number of row bands per host-pointer call (0 = automatic) */
@@ -550,7 +551,7 @@ extern "C" int lumacu_destroy(lumacu_ctx *ctx)
             if (b->p)
                 cudaFree(b->p);
     for (DeviceBuffer *b : {&ctx->d_tables, &ctx->d_pq, &ctx->d_vd, &ctx->d_pqh, &ctx->d_rgb, &ctx->d_planes, &ctx->d_stats,
-                            &ctx->d_aux})
+                            &ctx->d_aux, &ctx->d_half})
         if (b->p)
             cudaFree(b->p);
     if (ctx->h_pin)
@@ -1611,7 +1612,7 @@ try {
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const size_t n = (size_t)w * h;
     const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
-    launch_half_rgba_to_frame(blocks, st, d_rgba_half, d_rgb, n, channels);
+    launch_half_rgba_to_frame(blocks, st, d_rgba_half, d_rgb, n, n, channels);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -1631,7 +1632,7 @@ try {
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const size_t n = (size_t)w * h;
     const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
-    launch_frame_to_half_rgba(blocks, st, d_rgb, d_rgba_half, n);
+    launch_frame_to_half_rgba(blocks, st, d_rgb, d_rgba_half, n, n);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return LUMACU_OK;
@@ -1891,23 +1892,28 @@ static int ensure_async_state(lumacu_ctx *ctx)
     return LUMACU_OK;
 }
 
+/* half_src != NULL: the frame arrives as interleaved half-float RGBA pixels (Imf::Rgba, 8 B/px over PCIe instead of 12) and
+ * is expanded on the device by ExrInterface::readFrame's pixel loop (half_channels = Imf::RgbaChannels) band by band;
+ * rgb is unused then. */
 static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,
                        uint8_t *const planes[3], const int32_t strides[3], int write_back, lumacu_frame_stats *stats,
-                       bool passthrough, bool async = false)
+                       bool passthrough, bool async = false, const void *half_src = nullptr, int half_channels = 7)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
         return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_encode: lumacu_set_quantizer has not been called");
-    if (!rgb || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
+    if ((!rgb && !half_src) || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode: NULL pointer argument");
+    if (half_src && half_channels != 1 && half_channels != 2 && half_channels != 4 && half_channels != 7 && half_channels != 15)
+        return fail(ctx, LUMACU_ERR_UNSUPPORTED, "Reading of luminance only frames not yet supported"); /* src/exr_interface.cpp:138-140 */
     int rc = check_profile(ctx, profile, w, h, true);
     if (rc)
         return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
         return rc;
-    note_if_pageable(ctx, rgb, "the frame passed to lumacu_encode");
+    note_if_pageable(ctx, half_src ? half_src : (const void *)rgb, "the frame passed to lumacu_encode");
     note_if_pageable(ctx, planes[0], "the plane buffer passed to lumacu_encode");
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
@@ -1922,7 +1928,8 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
     device_plane_layout(w, h, profile, dstride, off, &ptotal);
     const int nb = band_count(ctx, w, h);
     if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) ||
-        (rc = reserve(ctx, ctx->d_stats, sizeof(lumacu_frame_stats) * 64)) || (rc = ensure_events(ctx, nb)))
+        (rc = reserve(ctx, ctx->d_stats, sizeof(lumacu_frame_stats) * 64)) || (rc = ensure_events(ctx, nb)) ||
+        (half_src && (rc = reserve(ctx, ctx->d_half, npx * 8))))
         return rc;
     float *d_rgb = (float *)ctx->d_rgb.p;
     uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
@@ -1934,13 +1941,24 @@ static int host_encode(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int 
     DrainUnlessQueued drain(ctx);
     for (int b = 0; b < nb; b++) {
         const uint32_t y0 = band_row(h, nb, b), y1 = band_row(h, nb, b + 1), rows = y1 - y0;
-        /* the band's rows of the three planes in one strided copy (pitch = one plane) */
-        CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb + (size_t)y0 * w, npx * 4, rgb + (size_t)y0 * w, npx * 4, (size_t)rows * w * 4, 3,
-                                      cudaMemcpyHostToDevice, ctx->s_in));
+        if (half_src) /* the band's pixels are contiguous */
+            CU_TRY(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_half.p + (size_t)y0 * w * 8, (const uint8_t *)half_src + (size_t)y0 * w * 8,
+                                        (size_t)rows * w * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        else /* the band's rows of the three planes in one strided copy (pitch = one plane) */
+            CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb + (size_t)y0 * w, npx * 4, rgb + (size_t)y0 * w, npx * 4, (size_t)rows * w * 4, 3,
+                                          cudaMemcpyHostToDevice, ctx->s_in));
         CU_TRY(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
         if (b == nb - 1 && !write_back)
             CU_TRY(ctx, cudaEventRecord(ctx->ev_input, ctx->s_in)); /* the caller's frame has been read completely */
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (half_src) {
+            const size_t n = (size_t)rows * w;
+            const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+            launch_half_rgba_to_frame(blocks, ctx->stream, (const uint8_t *)ctx->d_half.p + (size_t)y0 * w * 8, d_rgb + (size_t)y0 * w, n,
+                                      npx, half_channels);
+            CU_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
         const uint32_t cy0 = sub ? y0 >> 1 : y0;
         uint8_t *bp[3] = {dp[0] + (size_t)y0 * dstride[0], dp[1] + (size_t)cy0 * dstride[1], dp[2] + (size_t)cy0 * dstride[2]};
         float *band = d_rgb + (size_t)y0 * w;
@@ -1978,14 +1996,16 @@ try {
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
 
+/* half_dst != NULL: the decoded frame leaves as interleaved half-float RGBA pixels (ExrInterface::writeFrame's pixel loop
+ * run on the device band by band: 8 B/px over PCIe instead of 12); rgb is unused then. */
 static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w, uint32_t h,
-                       int profile, float pre_scaling, float *rgb, bool passthrough, bool async = false)
+                       int profile, float pre_scaling, float *rgb, bool passthrough, bool async = false, void *half_dst = nullptr)
 {
     if (!ctx)
         return LUMACU_ERR_INVALID_ARGUMENT;
     if (!ctx->configured)
         return fail(ctx, LUMACU_ERR_NOT_CONFIGURED, "lumacu_decode: lumacu_set_quantizer has not been called");
-    if (!rgb || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
+    if ((!rgb && !half_dst) || !planes || !strides || !planes[0] || !planes[1] || !planes[2])
         return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode: NULL pointer argument");
     int rc = check_profile(ctx, profile, w, h, false);
     if (rc)
@@ -1993,7 +2013,7 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if ((rc = finish_pending(ctx)) || (rc = ensure_async_state(ctx)))
         return rc;
-    note_if_pageable(ctx, rgb, "the frame passed to lumacu_decode");
+    note_if_pageable(ctx, half_dst ? (const void *)half_dst : (const void *)rgb, "the frame passed to lumacu_decode");
     note_if_pageable(ctx, planes[0], "the plane buffer passed to lumacu_decode");
     const size_t npx = (size_t)w * h;
     uint32_t pw[3], ph[3];
@@ -2008,7 +2028,8 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
     device_plane_layout(w, h, profile, dstride, off, &ptotal);
     /* the reference accepts odd decoded sizes in principle (plane dims are rounded up); bands need even rows */
     const int nb = (h % 2 == 0) ? band_count(ctx, w, h) : 1;
-    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) || (rc = ensure_events(ctx, nb)))
+    if ((rc = reserve(ctx, ctx->d_rgb, npx * 12)) || (rc = reserve(ctx, ctx->d_planes, ptotal)) || (rc = ensure_events(ctx, nb)) ||
+        (half_dst && (rc = reserve(ctx, ctx->d_half, npx * 8))))
         return rc;
     float *d_rgb = (float *)ctx->d_rgb.p;
     uint8_t *dp[3] = {(uint8_t *)ctx->d_planes.p + off[0], (uint8_t *)ctx->d_planes.p + off[1],
@@ -2034,10 +2055,21 @@ static int host_decode(lumacu_ctx *ctx, const uint8_t *const planes[3], const in
         rc = decode_launch(ctx, bp, dstride, w, rows, profile, pre_scaling, band, 1, 0, nullptr, ctx->stream, opt);
         if (rc)
             return rc;
+        if (half_dst) {
+            const size_t n = (size_t)rows * w;
+            const unsigned blocks = (unsigned)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+            launch_frame_to_half_rgba(blocks, ctx->stream, band, (uint8_t *)ctx->d_half.p + (size_t)y0 * w * 8, n, npx);
+            CU_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
         CU_TRY(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
-        CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3, cudaMemcpyDeviceToHost,
-                                      ctx->s_out));
+        if (half_dst)
+            CU_TRY(ctx, cudaMemcpyAsync((uint8_t *)half_dst + (size_t)y0 * w * 8, (const uint8_t *)ctx->d_half.p + (size_t)y0 * w * 8,
+                                        (size_t)rows * w * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        else
+            CU_TRY(ctx, cudaMemcpy2DAsync(rgb + (size_t)y0 * w, npx * 4, band, npx * 4, (size_t)rows * w * 4, 3, cudaMemcpyDeviceToHost,
+                                          ctx->s_out));
     }
     drain.queued = true;
     ctx->pending = true;
@@ -2052,6 +2084,26 @@ try {
     return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, rgb, false);
 }
 LUMACU_CATCH(const_cast<lumacu_ctx *>(ctx))
+
+/* ---- EXR-sourced / EXR-bound frames without the f32 detour over PCIe ---------------------------------------------- */
+extern "C" int lumacu_encode_half_rgba(lumacu_ctx *ctx, const void *rgba_half, uint32_t w, uint32_t h, int channels, int profile,
+                                       float pre_scaling, uint8_t *const planes[3], const int32_t strides[3],
+                                       lumacu_frame_stats *stats)
+try {
+    if (ctx && !rgba_half)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_encode_half_rgba: NULL pointer argument");
+    return host_encode(ctx, nullptr, w, h, profile, pre_scaling, planes, strides, 0, stats, false, false, rgba_half, channels);
+}
+LUMACU_CATCH(ctx)
+
+extern "C" int lumacu_decode_half_rgba(lumacu_ctx *ctx, const uint8_t *const planes[3], const int32_t strides[3], uint32_t w,
+                                       uint32_t h, int profile, float pre_scaling, void *rgba_half)
+try {
+    if (ctx && !rgba_half)
+        return fail(ctx, LUMACU_ERR_INVALID_ARGUMENT, "lumacu_decode_half_rgba: NULL pointer argument");
+    return host_decode(ctx, planes, strides, w, h, profile, pre_scaling, nullptr, false, false, rgba_half);
+}
+LUMACU_CATCH(ctx)
 
 /* ---- asynchronous pair: queue the call, return; lumacu_wait_input / lumacu_wait complete it ------------------ */
 extern "C" int lumacu_encode_async(lumacu_ctx *ctx, float *rgb, uint32_t w, uint32_t h, int profile, float pre_scaling,

@@ -217,3 +217,61 @@ print("done")
     quiet = subprocess.run([sys.executable, "-c", prog, "pageable"], capture_output=True, text=True, timeout=300,
                            env=dict(env, LUMACU_QUIET="1"))
     assert quiet.returncode == 0 and "pageable host memory" not in quiet.stderr
+
+
+@pytest.mark.parametrize("w,h,profile,cs,channels", [(1920, 1080, 2, "LUV", 7), (1280, 722, 3, "YCBCR", 15), (514, 258, 0, "LUV", 2)])
+def test_half_rgba_host_entry_points(lumalib, po, w, h, profile, cs, channels):
+    """lumacu_encode_half_rgba / lumacu_decode_half_rgba: the EXR pixel loops (src/exr_interface.cpp:73-143, :157-187) run on
+    the device inside the banded pipeline, 8 B/px over the bus.  Planes equal those of the reference's sequence (expand
+    the half pixels on the host, then encode -- checked against our float entry point AND the CPU oracle); decoded pixels
+    equal decode followed by the float -> half rounding of Imf's half (= numpy's float16 cast), alpha 0."""
+    L = lumalib
+    bits = 8 if profile < 2 else 11
+    cb = 8 if profile < 2 else 10
+    enc = L.LumaEncoder()
+    enc.setParams(L.LumaEncoderParams(ptf="PQ", ptfBitDepth=bits, colorSpace=cs, colorBitDepth=cb, profile=profile,
+                                      bitDepth=8 if profile < 2 else 12))
+    enc.initialize(None, w, h)
+    dec = L.LumaDecoder()
+    dec.setParams(L.LumaDecoderParams(ptf=L.PTF_PQ, colorSpace=enc.getParams().colorSpace, ptfBitDepth=bits, colorBitDepth=cb,
+                                      profile=profile))
+    dec.initialize()
+    rng = np.random.default_rng(w + profile)
+    rgba = np.empty((h, w, 4), dtype=np.float16)
+    rgba[..., :3] = np.moveaxis(po.noise_frame(w, h, seed=31), 0, -1).astype(np.float16)
+    rgba[..., 3] = 1.0
+    k = rng.integers(0, h * w, 3000)
+    rgba.reshape(-1, 4)[k, rng.integers(0, 3, k.size)] = rng.choice(
+        np.array([0.0, -0.0, 6e-8, 6.1e-5, 65504.0, np.inf, -np.inf, np.nan, -1.0], np.float16), k.size)
+    f = rgba.astype(np.float32)
+    if channels in (7, 15):
+        frame = np.ascontiguousarray(np.stack([f[..., 0], f[..., 1], f[..., 2]]))
+    else:
+        frame = np.ascontiguousarray(np.stack([f[..., {1: 0, 2: 1, 4: 2}[channels]]] * 3))
+    nbytes = 2 if profile > 1 else 1
+    o = po.Oracle().setQuantizer("PQ", bits, cs, cb)
+    ref_planes, _ = o.encode(frame.copy(), profile, 1.0)
+    for bands in (1, 5, 0):
+        _set_bands(L, enc, bands)
+        _set_bands(L, dec, bands)
+        want = [p.copy() for p in enc.encode(frame.copy(), L.alloc_planes(w, h, profile))]
+        want_stats = dict(enc.last_stats)
+        got = enc.encode_half_rgba(rgba, channels, L.alloc_planes(w, h, profile))
+        for p, (a, b, c, (pw, ph)) in enumerate(zip(got, want, ref_planes, po.plane_dims(w, h, profile))):
+            assert np.array_equal(a, b), f"bands={bands}: plane {p} differs from the float entry point"
+            assert np.array_equal(a[:ph, :pw * nbytes], c[:ph, :pw * nbytes]), f"bands={bands}: plane {p} differs from the oracle"
+        assert enc.last_stats["max"] == want_stats["max"] and enc.last_stats["min"] == want_stats["min"]
+        out = dec.decode(got, w, h).copy()
+        half = dec.decode_half_rgba(got, w, h)
+        with np.errstate(over="ignore", invalid="ignore"):
+            ref_half = np.stack([out[0], out[1], out[2], np.zeros_like(out[0])], axis=-1).astype(np.float16)
+        assert np.array_equal(half.view(np.uint16), ref_half.view(np.uint16)), f"bands={bands}: half pixels differ"
+
+
+def test_half_rgba_rejects_luminance_only_files(lumalib):
+    L = lumalib
+    enc = L.LumaEncoder()
+    enc.setParams(L.LumaEncoderParams(profile=2, bitDepth=12))
+    enc.initialize(None, 64, 32)
+    with pytest.raises(L.LumaException, match="luminance only"):
+        enc.encode_half_rgba(np.zeros((32, 64, 4), np.float16), channels=16)
