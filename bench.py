@@ -86,6 +86,16 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def host_cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_cpu_baseline(frames_per_worker: int, workers: int | None = None) -> dict:
     """The reference's CPU path in a separate process tree (never shares a process with CUDA)."""
     workers = workers or host_cores()
@@ -131,7 +141,8 @@ def reference_arm(args):
         "note": "reference CPU implementation (LumaEncoder::encode + LumaDecoder::decode, VP9 stubbed out), one independent "
                 f"frame stream per host core; each step = {res['cores'] * args.cpu_frames} frames of the workload",
         "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": res["cores"], "kind": res["kind"],
-                         "sample": res["sample"], "per_core_mpx_s": res["per_core_mpx_s"], "library": ref_so},
+                         "sample": res["sample"], "per_core_mpx_s": res["per_core_mpx_s"], "library": ref_so,
+                         "cpu_model": host_cpu_model()},
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -790,7 +801,8 @@ def ours_arm(args):
             line["configs"] = configs
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": "Mpixels/s", "cores": cpu["cores"], "kind": cpu["kind"],
-                                    "sample": cpu["sample"], "per_core_mpx_s": cpu["per_core_mpx_s"]}
+                                    "sample": cpu["sample"], "per_core_mpx_s": cpu["per_core_mpx_s"],
+                                    "cpu_model": host_cpu_model()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
