@@ -1231,7 +1231,11 @@ int grid_for(lumacu_ctx *ctx, const void *fn, size_t smem, uint32_t ntiles, uint
     if (it != ctx->occupancy.end() && it->second.first == smem) {
         per_sm = it->second.second;
     } else {
-        if (smem > 48 * 1024)
+        /* the 48 KB default limit covers dynamic + STATIC shared memory (mbarrier, powf tables, reduction scratch):
+         * 48 KB of tables exactly (e.g. a 13-bit LUT + a 12-bit chroma table) already needs the opt-in */
+        cudaFuncAttributes fa;
+        CU_TRY(ctx, cudaFuncGetAttributes(&fa, fn));
+        if (smem + fa.sharedSizeBytes > 48 * 1024)
             CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem));
         if (per_sm < 1)
@@ -1719,7 +1723,7 @@ try {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const void *fn = quantize_kernel_ptr();
-    if (ctx->smem_enc > 48 * 1024)
+    if (ctx->smem_enc > 32 * 1024) /* the 48 KB default also has to hold the kernel's static shared memory */
         CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_enc));
     const uint32_t blocks = (uint32_t)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 4);
     launch_quantize(blocks, ctx->smem_enc, st, ctx->q, d_in, d_out, n, channel_uses_lut(ctx, ch) ? 1 : 0);

@@ -190,7 +190,8 @@ def test_ragged_sizes_and_unaligned_pitches(L, po, w, h, profile):
 
 @pytest.mark.parametrize("ptf,bits,cbits", [("PQ", 10, 10), ("PQ", 12, 12), ("LOG", 12, 8), ("LOG", 11, 12), ("PSI", 11, 8),
                                             ("PSI", 8, 8), ("JND_HDRVDP", 12, 8), ("JND_HDRVDP", 10, 10), ("LINEAR", 11, 8),
-                                            ("LINEAR", 12, 8), ("PQ", 16, 16), ("PQ", 14, 9), ("PQ", 1, 1)])
+                                            ("LINEAR", 12, 8), ("PQ", 16, 16), ("PQ", 14, 9), ("PQ", 1, 1),
+                                            ("PQ", 13, 12)])  # 13/12 bits: the decode tables fill 48 KB of shared memory exactly
 def test_transfer_functions_and_bit_depths(L, po, ptf, bits, cbits):
     enc, o = make_pair(L, po, ptf=ptf, bits=bits, cbits=cbits)
     frame = adversarial_frame(256, 64, lut=o.getMapping(), seed=bits)
@@ -455,6 +456,48 @@ def test_unfused_halves_equal_fused(L, po, cs, profile):
     assert dec.m_quant.transformColorSpace(half, False, sc)
     assert max_ulp(half, want) <= FLOAT_ULP_TOL[cs]
     assert max_ulp(dec.decode(ref_planes, w, h), want) <= FLOAT_ULP_TOL[cs]
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("LUMA_FUZZ_SEEDS", "6"))))
+def test_random_configurations(L, po, seed):
+    """Seeded sweep over what the parametrised cases above leave unexplored in combination: every colour space x profile
+    x transfer function x bit depths x luminance range x preScaling x frame size (ragged ones included) x plane pitch,
+    20 draws per seed, each through check_frame (four encode kernel paths, two decode paths, statistics, side effect).
+    LUMA_FUZZ_SEEDS=N widens the sweep (6 seeds in the regular suite)."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(20):
+        cs = CS[rng.integers(0, 4)]
+        profile = int(rng.integers(0, 4))
+        ptf = ("PQ", "LOG", "PSI", "JND_HDRVDP", "LINEAR")[rng.integers(0, 5)]
+        if profile < 2:
+            bits, cbits = 8, int(rng.integers(1, 9))
+        elif ptf in ("PSI", "JND_HDRVDP"):
+            bits, cbits = int(rng.choice([10, 11, 12])), int(rng.integers(6, 13))   # the shipped tables
+        else:
+            bits, cbits = int(rng.integers(2, 15)), int(rng.integers(2, 13))
+        lmax = float(rng.choice([100.0, 1000.0, 4000.0, 1e4]))
+        lmin = float(rng.choice([0.001, 0.005, 0.01, 0.5]))
+        sc = float(rng.choice([1.0, 1.0, 20.0, 0.37]))
+        sub = profile in (0, 2)
+        w = int(rng.integers(1, 160)) * 2   # LumaEncoder::initialize takes even sizes only, whatever the profile
+        h = int(rng.integers(1, 90)) * 2
+        if rng.random() < 0.3:
+            w = ((w + 127) // 128) * 128  # whole warps per row: the vector / tensor-map friendly shapes
+        enc, o = make_pair(L, po, ptf=ptf, bits=bits, cs=cs, cbits=cbits, profile=profile, sc=sc, lmax=lmax, lmin=lmin)
+        frame = adversarial_frame(w, h, lut=o.getMapping(), seed=int(rng.integers(1 << 30))) if w * h >= 400 else \
+            po.noise_frame(w, h, seed=int(rng.integers(1 << 30)))
+        with np.errstate(over="ignore"):
+            frame = np.ascontiguousarray(frame / np.float32(sc))
+        strides = None
+        if rng.random() < 0.5:
+            nbytes = 2 if profile > 1 else 1
+            cw = (w + 1) // 2 if sub else w
+            strides = [w * nbytes + int(rng.integers(0, 70)), cw * nbytes + int(rng.integers(0, 70)), cw * nbytes + int(rng.integers(0, 70))]
+        try:
+            check_frame(L, po, frame, enc, o, profile, sc, cs, strides=strides)
+        except AssertionError as e:
+            raise AssertionError(f"cs={cs} profile={profile} ptf={ptf} bits={bits}/{cbits} lmax={lmax} lmin={lmin} sc={sc} "
+                                 f"{w}x{h} strides={strides}: {e}") from e
 
 
 def test_set_quantizer_rejects_untrusted_sizes(L):
