@@ -98,6 +98,79 @@ def test_full_size_properties(lumalib, po, torch_cuda, w, h):
         assert st["max"][f] == pytest.approx(float(y.max()), rel=1e-5)
 
 
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("LUMA_FUZZ_SEEDS", "4"))))
+def test_random_batches_on_the_device_api(lumalib, po, torch_cuda, seed):
+    """Seeded sweep through the device-pointer entry points (multi-frame launches): random colour space, profile, PTF, bit
+    depths, range, preScaling, frame count, frame size, plane pitches, with and without statistics -- tuned kernels ==
+    generic kernels on every byte (encode) / bit (decode, incl. random out-of-range codes), and one frame of each draw
+    against the CPU oracle.  LUMA_FUZZ_SEEDS=N widens the sweep."""
+    torch = torch_cuda
+    from lumahdrv_b200.device import DeviceTransform
+    from lumahdrv_b200 import vpx_strides
+
+    rng = np.random.default_rng(5000 + seed)
+    for _ in range(12):
+        cs = ("LUV", "RGB", "YCBCR", "XYZ")[rng.integers(0, 4)]
+        profile = int(rng.integers(0, 4))
+        ptf = ("PQ", "LOG", "PQ", "LINEAR")[rng.integers(0, 4)]
+        bits, cbits = (8, int(rng.integers(2, 9))) if profile < 2 else (int(rng.integers(6, 17)), int(rng.integers(4, 15)))
+        lmax = float(rng.choice([1000.0, 4000.0, 1e4]))
+        sc = float(rng.choice([1.0, 1.0, 20.0]))
+        sub = profile in (0, 2)
+        n = int(rng.integers(1, 5))
+        w = int(rng.integers(1, 300)) * 2 if rng.random() < 0.6 else int(rng.integers(1, 9)) * 128
+        h = int(rng.integers(1, 120)) * 2
+        what = f"cs={cs} profile={profile} ptf={ptf} bits={bits}/{cbits} lmax={lmax} sc={sc} n={n} {w}x{h}"
+        t = DeviceTransform(0, ptf=ptf, ptfBitDepth=bits, colorSpace=cs, colorBitDepth=cbits, maxLum=lmax, minLum=0.005,
+                            profile=profile, preScaling=sc)
+        ctx = t.quant.ctx
+        frames = [np.ascontiguousarray(po.noise_frame(w, h, seed=int(rng.integers(1 << 30))) / np.float32(sc)) for _ in range(n)]
+        k = rng.integers(0, frames[0].size, 64)
+        frames[0].reshape(-1)[k] = rng.choice(np.array([0.0, -1.0, np.nan, np.inf, 1e-45, 3e38, 1e-4, 1e8], np.float32), k.size)
+        rgb = torch.from_numpy(np.stack(frames)).cuda()
+        strides = None
+        if rng.random() < 0.5:
+            strides = [int(s) + int(rng.integers(0, 5)) * 16 for s in vpx_strides(w, profile)]
+        use_stats = rng.random() < 0.5
+        nbytes = 2 if profile > 1 else 1
+        results = []
+        for path in (1, 0):
+            ctx.set_kernel_path(path)
+            planes = t.alloc_planes(n, w, h, strides)
+            stats = t.alloc_stats(n) if use_stats else None
+            t.encode(rgb, planes=planes, stats=stats)
+            results.append((planes, t.stats_to_numpy(stats) if use_stats else None))
+        for p, (a, b) in enumerate(zip(results[0][0], results[1][0])):
+            assert torch.equal(a, b), f"{what}: encode plane {p}: tuned and generic kernels differ in {(a != b).sum().item()} bytes"
+        if use_stats:
+            for key in ("max", "min"):
+                assert np.array_equal(results[0][1][key], results[1][1][key], equal_nan=True), f"{what}: stats {key}"
+        o = po.Oracle().setQuantizer(ptf, bits, cs, cbits, lmax, 0.005)
+        f = int(rng.integers(0, n))
+        ref_planes, _ = o.encode(frames[f].copy(), profile, sc)
+        for p, (a, b, (pw, ph)) in enumerate(zip(results[1][0], ref_planes, po.plane_dims(w, h, profile))):
+            assert np.array_equal(a[f].cpu().numpy()[:ph, :pw * nbytes], b[:ph, :pw * nbytes]), f"{what}: frame {f} plane {p} vs the oracle"
+        # decode: the encoder's planes, then planes of random code words (any 16-bit / 8-bit pattern)
+        for trial in range(2):
+            planes = results[1][0]
+            if trial == 1:
+                planes = [torch.from_numpy(rng.integers(0, 256, size=tuple(p.shape), dtype=np.uint8)).cuda() for p in planes]
+            outs = []
+            for path in (1, 0):
+                ctx.set_kernel_path(path)
+                outs.append(t.decode(planes, w, h).clone())
+            assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)), f"{what}: decode trial {trial}: tuned != generic"
+            host = [p[f].cpu().numpy() for p in planes]
+            ref = o.decode(host, w, h, profile, sc)
+            got = outs[1][f].cpu().numpy()
+            if cs == "YCBCR":
+                from conftest import max_ulp
+                assert max_ulp(got, ref) <= 1, f"{what}: decode trial {trial} vs the oracle"
+            else:
+                assert bits_equal(got, ref), f"{what}: decode trial {trial} vs the oracle"
+        ctx.set_kernel_path(0)
+
+
 @pytest.mark.parametrize("w,h,n", [(3840, 2160, 3), (7680, 4320, 2)])
 def test_whole_frames_of_a_batch_equal_the_oracle(lumalib, po, torch_cuda, w, h, n):
     """Whole 4K / 8K noise frames through the multi-frame launch (the grid geometry bench.py times), every byte of every
