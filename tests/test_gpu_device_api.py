@@ -171,6 +171,54 @@ def test_random_batches_on_the_device_api(lumalib, po, torch_cuda, seed):
         ctx.set_kernel_path(0)
 
 
+def test_frame_larger_than_32_bit_offsets(lumalib, po, torch_cuda):
+    """Maximum sizes: a 32768 x 40000 frame (1.31 Gpx, 15.7 GB of f32; byte offsets inside a plane pass 2^32, so the tuned
+    kernels' 32-bit offsets do not apply and the generic kernels index with 64 bits).  Bands of rows at the start, either
+    side of the 2^32-byte mark and at the very end against the oracle; a frame of more than 2^31 - 1 pixels is refused."""
+    torch = torch_cuda
+    from lumahdrv_b200.device import DeviceTransform
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 << 30:
+        pytest.skip("needs 70 GB of free device memory")
+    w, h = 32768, 40000
+    t = DeviceTransform(0)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    rgb = torch.empty((1, 3, h, w), dtype=torch.float32, device="cuda")
+    for c in range(3):  # plane by plane: no 15 GB temporaries
+        for y0 in range(0, h, 4000):
+            u = torch.rand((4000, w), generator=g, device="cuda", dtype=torch.float32)
+            rgb[0, c, y0:y0 + 4000] = 0.005 * torch.pow(torch.tensor(2.0e6, device="cuda"), u)
+    del u
+    stats = t.alloc_stats(1)
+    planes = t.encode(rgb, stats=stats)
+    assert t.quant.ctx.last_kernel_path == 0
+    dec = t.decode(planes, w, h)
+    o = po.Oracle().setQuantizer("PQ", 11, "LUV", 8)
+    row_4g = (1 << 32) // (4 * w)  # the row whose first float sits 2^32 bytes into its plane
+    for start in (0, row_4g - 8, row_4g, h - 16):
+        rows = slice(start, start + 16)
+        band = rgb[0, :, rows, :].cpu().numpy().copy()
+        ref_planes, _ = o.encode(band, 2, 1.0)
+        assert np.array_equal(planes[0][0, rows, : 2 * w].cpu().numpy(), ref_planes[0][:, : 2 * w]), f"rows {start}.."
+        crow = slice(rows.start // 2, rows.stop // 2)
+        assert np.array_equal(planes[1][0, crow, :w].cpu().numpy(), ref_planes[1][:, :w]), f"rows {start}.."
+        assert np.array_equal(planes[2][0, crow, :w].cpu().numpy(), ref_planes[2][:, :w]), f"rows {start}.."
+        assert bits_equal(dec[0, :, rows, :].cpu().numpy(), o.decode(ref_planes, w, 16, 2, 1.0)), f"rows {start}.."
+    st = t.stats_to_numpy(stats)
+    assert 0.005 * 0.2 < st["min"][0] < 0.02 and 5e3 < st["max"][0] <= 1.0001e4 and np.isfinite(st["sum"][0])
+    del rgb, dec, planes
+    torch.cuda.empty_cache()
+    # 46342 x 46342 = 2 147 580 964 pixels > 2^31 - 1: refused before anything is touched
+    from lumahdrv_b200._lib import lib
+    import ctypes as C
+    dummy = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ptrs = (C.c_void_p * 3)(dummy.data_ptr(), dummy.data_ptr(), dummy.data_ptr())
+    strides = (C.c_int32 * 3)(46342 * 2, 46342, 46342)
+    fstr = (C.c_size_t * 3)(0, 0, 0)
+    rc = lib().lumacu_encode_dev(t.quant.ctx.handle, dummy.data_ptr(), None, 46342, 46342, 2, 1.0, ptrs, strides, 1, 0, fstr, None, None)
+    assert rc != 0 and b"too large" in lib().lumacu_last_error(t.quant.ctx.handle)
+
+
 @pytest.mark.parametrize("w,h,n", [(3840, 2160, 3), (7680, 4320, 2)])
 def test_whole_frames_of_a_batch_equal_the_oracle(lumalib, po, torch_cuda, w, h, n):
     """Whole 4K / 8K noise frames through the multi-frame launch (the grid geometry bench.py times), every byte of every
