@@ -95,7 +95,7 @@ __device__ __forceinline__ float div_const_int(float x)
 __device__ __forceinline__ float pq_encode(float val, float l_max)
 {
     const float m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
-    float Lp = powf_glibc(__fdiv_rn(val, l_max), n);
+    float Lp = powf_glibc<true>(__fdiv_rn(val, l_max), n);
     float num = __fadd_rn(c1, __fmul_rn(c2, Lp));
     float den = __fadd_rn(1.0f, __fmul_rn(c3, Lp));
     return powf_glibc(__fdiv_rn(num, den), m);
@@ -105,7 +105,7 @@ __device__ __forceinline__ float pq_decode(float val, float l_max)
     const float m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
     const float inv_m = 1.0f / m; /* evaluated in fp32 like the reference's 1.0f/m */
     const float inv_n = 1.0f / n;
-    float Vp = powf_glibc(val, inv_m);
+    float Vp = powf_glibc<true>(val, inv_m);
     float num = fmaxf(0.0f, __fsub_rn(Vp, c1)); /* std::max(0.0f, x): NaN -> 0 */
     float den = __fsub_rn(c2, __fmul_rn(c3, Vp));
     return __fmul_rn(l_max, powf_glibc(__fdiv_rn(num, den), inv_n));

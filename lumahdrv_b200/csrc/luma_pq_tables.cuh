@@ -2,8 +2,8 @@
  * luma_pq_tables.cuh -- exhaustive, L2-resident tables of the two PQ curves for CS_YCBCR.
  *
  * CS_YCBCR evaluates PQ per pixel through libm powf (reference src/luma_quantizer.cpp:331-337,447-459,485-501): eight
- * calls per pixel each way.  powf_glibc.cuh reproduces the host libm bit for bit, but one call is ~110 instructions
- * (27 of them unfused FP64).  Two of the call sites have a SMALL domain once you look at what feeds them, so their
+ * calls per pixel each way.  powf_glibc.cuh reproduces the host libm bit for bit, but one call is ~45 instructions
+ * (18 of them FP64, at a quarter of the fp32 rate).  Two of the call sites have a SMALL domain once you look at what feeds them, so their
  * results can be tabulated for EVERY possible input, with the exact device powf, once per quantizer:
  *
  *  (1) PQ decode, L * powf(max(0, Vp - c1) / (c2 - c3 Vp), 1/n) with Vp = powf(v, 1/m), is only ever applied to
@@ -123,7 +123,7 @@ __device__ __forceinline__ float pq_decode_tab(const QuantDev &q, float v, float
 __device__ __forceinline__ float pq_encode_tab(const QuantDev &q, float val, float l_max)
 {
     const float m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
-    const float Lp = powf_glibc(__fdiv_rn(val, l_max), n);
+    const float Lp = powf_glibc<true>(__fdiv_rn(val, l_max), n);
     const float num = __fadd_rn(c1, __fmul_rn(c2, Lp));
     const float den = __fadd_rn(1.0f, __fmul_rn(c3, Lp));
     const float b = __fdiv_rn(num, den);

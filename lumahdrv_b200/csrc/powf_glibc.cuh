@@ -9,12 +9,15 @@
  * powf nor a double-precision pow reproduces its bits.  This header restates
  * the published algorithm: log2(x) from a 16-entry {1/c, log2 c} table plus a
  * degree-5 polynomial, times y, then exp2 through a 32-entry 2^(i/32) table
- * and a cubic, all in IEEE double with SEPARATE multiplies and adds (no FMA),
- * which is what the host executes (hard part 3: a CPU replay of this
- * sequence matched the host powf in 1.2e9 of 1.2e9 PQ-domain calls on glibc
- * 2.39-0ubuntu8.5).  tests/test_gpu_parity.py::test_ycbcr_powf_dense checks the
- * device function against the host libm through the YCbCr transform on ~3e7
- * powf evaluations spanning 1e-12 .. 1e6 plus the special values.
+ * and a cubic, all in IEEE double with every a*b+c FUSED, which is what the
+ * host executes (glibc's ifunc picks its FMA build on every CPU with FMA and
+ * AVX2).  scripts/powchk.c proves it by exhaustion: equal to the host powf
+ * (glibc 2.39-0ubuntu8.5) for every positive normal float and each of the four
+ * PQ exponents, 8.5e9 evaluations, 0 mismatches
+ * (profiles/r02_powf_exhaustive.log).  tests/test_gpu_parity.py::
+ * test_ycbcr_powf_dense checks the device function against the host libm
+ * through the YCbCr transform on ~3e7 evaluations spanning 1e-12 .. 1e6 plus
+ * the special values.
  *
  * Restricted to what the PQ call sites need: y is a finite, positive,
  * non-integer constant (0.1593f, 78.8438f and their fp32 reciprocals); x is
@@ -79,7 +82,18 @@ static __device__ __noinline__ float powf_glibc_rare(float x, float y);
 
 /* Straight-line main path: rare inputs are detected up front and recomputed out of line at the end, results that
  * overflow or underflow only override the value, so that the compiler can interleave the independent powf chains
- * of a pixel (three PQ curves at a time) instead of serialising them behind branches. */
+ * of a pixel (three PQ curves at a time) instead of serialising them behind branches.
+ *
+ * Every a*b+c of the published algorithm is ONE fused multiply-add here.  That is what the host executes: glibc selects
+ * its FMA build of this function (__powf_fma, sysdeps/x86_64/fpu/multiarch/e_powf.c) on every CPU with FMA + AVX2 --
+ * every B200 host -- and scripts/powchk.c compares both contraction choices with the host powf for EVERY positive normal
+ * float and the four PQ exponents (4 x 2 130 706 432 inputs, profiles/r02_powf_exhaustive.log): the fused sequence
+ * equals libm on all of them; the unfused one (rounds 1 and early 2 of this file, 27 operations instead of 18) differs
+ * for one input each of y = 1/0.1593f (x = 0x1.7b1e06p-11, reachable by PQ decode) and y = 78.8438f (x > 1, not
+ * reachable).
+ * RANGE_CHECK = false: for callers whose exponent cannot overflow or underflow a positive normal x (|y| < 0.85:
+ * 0.1593f and 1/78.8438f), the |y log2 x| >= 126 test is dropped. */
+template <bool RANGE_CHECK = true>
 __device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
 {
     /* log2_inline: x = 2^k z, z in [OFF, 2 OFF), c near the centre of z's subinterval */
@@ -92,15 +106,15 @@ __device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
     const double z = (double)__uint_as_float(iz);
 
     const double A0 = k_powf_poly[0], A1 = k_powf_poly[1], A2 = k_powf_poly[2], A3 = k_powf_poly[3], A4 = k_powf_poly[4];
-    const double r = __dadd_rn(__dmul_rn(z, tc.x), -1.0);
+    const double r = __fma_rn(z, tc.x, -1.0);
     const double y0 = __dadd_rn(tc.y, (double)k);
     const double r2 = __dmul_rn(r, r);
-    double yy = __dadd_rn(__dmul_rn(A0, r), A1);
-    const double p = __dadd_rn(__dmul_rn(A2, r), A3);
+    double yy = __fma_rn(A0, r, A1);
+    const double p = __fma_rn(A2, r, A3);
     const double r4 = __dmul_rn(r2, r2);
-    double q = __dadd_rn(__dmul_rn(A4, r), y0);
-    q = __dadd_rn(__dmul_rn(p, r2), q);
-    yy = __dadd_rn(__dmul_rn(yy, r4), q);
+    double q = __fma_rn(A4, r, y0);
+    q = __fma_rn(p, r2, q);
+    yy = __fma_rn(yy, r4, q);
 
     const double ylogx = __dmul_rn((double)y, yy);
 
@@ -114,30 +128,35 @@ __device__ __forceinline__ float powf_glibc_main(uint32_t ix, float y)
     unsigned long long t = s_exp2f_tab[ki & 31u];
     t += ki << (52 - 5);
     const double s = __longlong_as_double((long long)t);
-    const double zz = __dadd_rn(__dmul_rn(C0, rr), C1);
+    const double zz = __fma_rn(C0, rr, C1);
     const double rr2 = __dmul_rn(rr, rr);
-    double o = __dadd_rn(__dmul_rn(C2, rr), 1.0);
-    o = __dadd_rn(__dmul_rn(zz, rr2), o);
+    double o = __fma_rn(C2, rr, 1.0);
+    o = __fma_rn(zz, rr2, o);
     o = __dmul_rn(o, s);
     float res = __double2float_rn(o);
 
-    const uint32_t hi = (uint32_t)__double2hiint(ylogx) & 0x7fff8000u;
-    if (__builtin_expect(hi >= 0x405f8000u, 0)) { /* |y log2 x| >= 126 */
-        if (ylogx > 0x1.fffffffd1d571p+6)
-            res = __int_as_float(0x7f800000); /* overflow */
-        else if (ylogx <= -150.0)
-            res = 0.0f; /* underflow */
-        else if (ylogx < -149.0)
-            res = __int_as_float(0x00000001); /* __math_may_uflowf: 0x1.4p-75f squared */
+    if (RANGE_CHECK) {
+        const uint32_t hi = (uint32_t)__double2hiint(ylogx) & 0x7fff8000u;
+        if (__builtin_expect(hi >= 0x405f8000u, 0)) { /* |y log2 x| >= 126 */
+            if (ylogx > 0x1.fffffffd1d571p+6)
+                res = __int_as_float(0x7f800000); /* overflow */
+            else if (ylogx <= -150.0)
+                res = 0.0f; /* underflow */
+            else if (ylogx < -149.0)
+                res = __int_as_float(0x00000001); /* __math_may_uflowf: 0x1.4p-75f squared */
+        }
     }
     return res;
 }
 
+/* SMALL_EXPONENT: y is one of the two PQ exponents below 1 in magnitude (see RANGE_CHECK above).  Subnormal x still goes
+ * through the checked path (out of line). */
+template <bool SMALL_EXPONENT = false>
 __device__ __forceinline__ float powf_glibc(float x, float y)
 {
     const uint32_t ix = __float_as_uint(x);
     const bool rare = ix - 0x00800000u >= 0x7f800000u - 0x00800000u; /* not a positive normal number */
-    float res = powf_glibc_main(rare ? 0x3f800000u : ix, y);
+    float res = powf_glibc_main<!SMALL_EXPONENT>(rare ? 0x3f800000u : ix, y);
     if (__builtin_expect(rare, 0))
         res = powf_glibc_rare(x, y);
     return res;
@@ -155,7 +174,7 @@ static __device__ __noinline__ float powf_glibc_rare(float x, float y)
     ix = __float_as_uint(__fmul_rn(x, 0x1p23f));
     ix &= 0x7fffffffu;
     ix -= 23u << 23;
-    return powf_glibc_main(ix, y);
+    return powf_glibc_main<true>(ix, y);
 }
 
 } // namespace lumacu

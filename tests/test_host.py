@@ -239,3 +239,23 @@ def test_bench_cuda_arm_refuses_to_run_without_a_gpu():
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_device_powf_sequence_equals_host_libm(tmp_path):
+    """scripts/powchk.c replays the device's powf sequence (every a*b+c fused, IEEE double: powf_glibc.cuh) on the CPU and
+    compares it with the host libm's powf for every float of a range.  The committed log covers every positive normal
+    float for the four PQ exponents (profiles/r02_powf_exhaustive.log); here: the decades around the one input where the
+    unfused sequence of earlier rounds differed from libm (y = 1/0.1593f, x = 0x1.7b1e06p-11), and the PQ range of the
+    encode exponent.  Needs a host whose glibc runs its FMA build (any CPU with FMA + AVX2)."""
+    import shutil
+    import subprocess
+    flags = open("/proc/cpuinfo").read()
+    if " fma" not in flags or " avx2" not in flags:
+        pytest.skip("host CPU without FMA/AVX2: glibc runs its unfused powf build here")
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = tmp_path / "powchk"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", str(ROOT / "scripts" / "powchk.c"), "-lm", "-o", str(exe)], check=True)
+    for args in (["inv:0.1593", "1e-5", "1e-2"], ["0.1593", "1e-9", "2.0"], ["inv:78.8438", "0.01", "1.0"]):
+        out = subprocess.run([str(exe)] + args, check=True, capture_output=True, text=True).stdout
+        assert "FMA replay != libm: 0" in out.splitlines()[-1], out
