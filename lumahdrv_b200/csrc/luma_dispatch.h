@@ -54,6 +54,7 @@ const void *quantize_kernel_ptr();
 constexpr size_t kPqTabPqdBytes = (size_t)((0x3F800000u - 0x3B800000u + 1u + 31u) / 32u) * 16u;
 constexpr size_t kPqTabPqeBytes = (size_t)(0x3F8147AEu - 0x3F55C28Fu + 1u) * 4u;
 void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *pqe, float l_max);
+void launch_check_lmax_division(unsigned blocks, cudaStream_t st, float l_max, float rc, uint32_t *bad);
 /* v-keyed luma search table of CS_YCBCR encode: kVdTabBytes of device memory + one flag word (non-zero = unusable) */
 constexpr size_t kVdTabBytes = (size_t)((((0x3F800000u >> 13) - (0x3D000000u >> 13) + 1u) + 3u) & ~3u) * 4u;
 /* PQ encode of every half-float bit pattern (65 536 floats) for one preScaling / Lmax */

@@ -65,6 +65,10 @@ void launch_build_pq_tables(unsigned blocks, cudaStream_t st, void *pqd, float *
     build_pqd_kernel<<<blocks, 256, 0, st>>>((uint4 *)pqd, l_max);
     build_pqe_kernel<<<blocks, 256, 0, st>>>(pqe);
 }
+void launch_check_lmax_division(unsigned blocks, cudaStream_t st, float l_max, float rc, uint32_t *bad)
+{
+    check_lmax_division_kernel<<<blocks, 256, 0, st>>>(l_max, rc, bad);
+}
 void launch_build_pqh(cudaStream_t st, const QuantDev &q, float *tab, float sc, int prescale, float l_max)
 {
     build_pqh_kernel<<<64, 256, 0, st>>>(q, tab, sc, prescale, l_max);

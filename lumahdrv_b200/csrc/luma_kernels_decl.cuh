@@ -46,6 +46,10 @@ struct QuantDev {
     /* CS_YCBCR encode: direct search table keyed on v = (219 y' + 16)/255 (kVdEntries entries, luma_pq_tables.cuh (3));
      * NULL when it could not be built for this LUT */
     const uint32_t *vdtab;
+    /* CS_YCBCR encode: RN(1 / l_max) when val / l_max may be computed as q = val * rc, q += (val - q * l_max) * rc (two
+     * FMAs) -- proved equal to the IEEE quotient for EVERY float val >= 1e-10 by an exhaustive device check at
+     * set_quantizer time (luma_pq_tables.cuh check_lmax_division_kernel); 0 = divide */
+    float lmax_rc;
 };
 
 constexpr int kThreads = 256;

@@ -119,11 +119,37 @@ __device__ __forceinline__ float pq_decode_tab(const QuantDev &q, float v, float
     return pq_decode(v, l_max); /* below 2^-8, NaN, or an irregular bucket: the exact evaluation */
 }
 
+/* val / d with a precomputed rc = RN(1/d): q = RN(val rc), r = val - q d (exact in an FMA), RN(q + r rc).  Three
+ * instructions instead of the ~10 of an IEEE division; correctly rounded for "most" divisors and operands -- which
+ * ones is established by exhaustion, never assumed (below, and scripts/divchk.c for the compile-time divisor 255). */
+__device__ __forceinline__ float div_by_rc(float val, float d, float rc)
+{
+    const float qq = __fmul_rn(val, rc);
+    const float r = __fmaf_rn(-qq, d, val);
+    return __fmaf_rn(r, rc, qq);
+}
+#ifdef LUMA_PQ_TABLE_BUILDERS
+/* Every float val in [1e-10, FLT_MAX] (what max(c * sc, 1e-10f) can hand to PQ encode; +inf and NaN end as NaN either
+ * way, src/luma_quantizer.cpp:493-494): does div_by_rc give the bits of val / l_max?  1.35e9 inputs, under a
+ * millisecond. */
+__global__ void __launch_bounds__(256) check_lmax_division_kernel(float l_max, float rc, uint32_t *bad)
+{
+    const uint32_t lo = __float_as_uint(1e-10f), hi = 0x7f7fffffu;
+    bool differs = false;
+    for (uint64_t u = (uint64_t)lo + blockIdx.x * blockDim.x + threadIdx.x; u <= hi; u += (uint64_t)gridDim.x * blockDim.x) {
+        const float val = __uint_as_float((uint32_t)u);
+        differs |= __float_as_uint(div_by_rc(val, l_max, rc)) != __float_as_uint(__fdiv_rn(val, l_max));
+    }
+    if (differs)
+        atomicOr(bad, 1u);
+}
+#endif
+
 /* transformPQ(val, encode); identical to pq_encode(val, l_max) for every val */
 __device__ __forceinline__ float pq_encode_tab(const QuantDev &q, float val, float l_max)
 {
     const float m = 78.8438f, n = 0.1593f, c1 = 0.8359f, c2 = 18.8516f, c3 = 18.6875f;
-    const float Lp = powf_glibc<true>(__fdiv_rn(val, l_max), n);
+    const float Lp = powf_glibc<true>(q.lmax_rc != 0.0f ? div_by_rc(val, l_max, q.lmax_rc) : __fdiv_rn(val, l_max), n);
     const float num = __fadd_rn(c1, __fmul_rn(c2, Lp));
     const float den = __fadd_rn(1.0f, __fmul_rn(c3, Lp));
     const float b = __fdiv_rn(num, den);
@@ -218,15 +244,19 @@ static __device__ __noinline__ Float3x2 ycbcr_forward_px2_tab(const QuantDev &q,
         Bp0 = pq_encode_sample(q, p0.z, sc, prescale, l_max), Bp1 = pq_encode_sample(q, p1.z, sc, prescale, l_max);
     }
     const float y0 = dot3(0.2627f, 0.6780f, 0.0593f, Rp0, Gp0, Bp0), y1 = dot3(0.2627f, 0.6780f, 0.0593f, Rp1, Gp1, Bp1);
-    const float v0 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y0), 16.0f), 255.0f);
-    const float v1 = __fdiv_rn(__fadd_rn(__fmul_rn(219.0f, y1), 16.0f), 255.0f);
+    /* x / 255 by div_const_int<255>: exact whenever the quotient is a normal number or zero (scripts/divchk.c, all 2^32
+     * operands); the numerators here are 219 y' + 16 and 224 t + 128 with y', t = O(1): sums of floats of magnitude
+     * >= 16 resp. 128 ulps-of-128 apart, i.e. zero or >= 2^-17 in magnitude, never subnormal; NaN stays NaN.  (1.8814
+     * and 1.4746 do NOT qualify -- millions of mismatches -- and keep the IEEE division.) */
+    const float v0 = div_const_int<255>(__fadd_rn(__fmul_rn(219.0f, y0), 16.0f));
+    const float v1 = div_const_int<255>(__fadd_rn(__fmul_rn(219.0f, y1), 16.0f));
     Float3x2 c;
     c.a.x = LUMA_V ? v0 : pq_decode_tab(q, v0, l_max);
     c.b.x = LUMA_V ? v1 : pq_decode_tab(q, v1, l_max);
-    c.a.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp0, y0), 1.8814f)), 128.0f), 255.0f);
-    c.a.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp0, y0), 1.4746f)), 128.0f), 255.0f);
-    c.b.y = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp1, y1), 1.8814f)), 128.0f), 255.0f);
-    c.b.z = __fdiv_rn(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp1, y1), 1.4746f)), 128.0f), 255.0f);
+    c.a.y = div_const_int<255>(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp0, y0), 1.8814f)), 128.0f));
+    c.a.z = div_const_int<255>(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp0, y0), 1.4746f)), 128.0f));
+    c.b.y = div_const_int<255>(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Bp1, y1), 1.8814f)), 128.0f));
+    c.b.z = div_const_int<255>(__fadd_rn(__fmul_rn(224.0f, __fdiv_rn(__fsub_rn(Rp1, y1), 1.4746f)), 128.0f));
     return c;
 }
 

@@ -99,6 +99,8 @@ struct lumacu_ctx {
     int enc_variant = 0, dec_variant = 0; /* tuning sweep: which instantiation of the tuned kernels (0 = default) */
     int grid_cap = 0;                     /* tuning sweep: cap on resident blocks per SM (0 = occupancy) */
     int grid_tpt = 0;                     /* tuning sweep: tiles per thread of a multi-frame launch (0 = default) */
+    bool lmax_div_checked = false;        /* CS_YCBCR: val / Lmax by reciprocal + FMA verified for lmax_div_lmax (lmax_div_rc 0 = it is not exact) */
+    float lmax_div_lmax = 0.0f, lmax_div_rc = 0.0f;
     bool no_direct = false;               /* tuning sweep / tests: bucket + threshold search even when the direct table exists */
     bool global_direct = false;           /* tuning sweep / tests: read the (32-bit) direct table from global memory, no staging */
 
@@ -645,7 +647,34 @@ LUMACU_CATCH(nullptr)
 static int build_ycbcr_tables(lumacu_ctx *ctx, QuantDev &q, float max_lum)
 {
     q.pqd = nullptr, q.pqe = nullptr, q.vdtab = nullptr;
+    q.lmax_rc = 0.0f;
     ctx->pqh_valid = false; /* rebuilt by the next CS_YCBCR encode launch */
+    /* val / Lmax of PQ encode as a multiplication by the reciprocal plus one FMA correction -- only if that equals the
+     * IEEE quotient for every operand the path can produce, which the device checks by exhaustion (1.35e9 operands, < 1 ms;
+     * result cached per Lmax) */
+    if (max_lum > 0.0f && std::isfinite(max_lum)) {
+        if (!ctx->lmax_div_checked || memcmp(&ctx->lmax_div_lmax, &max_lum, sizeof(float)) != 0) {
+            ctx->lmax_div_checked = false;
+            if (reserve(ctx, ctx->d_vd, kVdTabBytes + 16) == LUMACU_OK) {
+                uint32_t *flag = (uint32_t *)((unsigned char *)ctx->d_vd.p + kVdTabBytes);
+                const float rc = 1.0f / max_lum;
+                uint32_t bad = 1;
+                CU_TRY(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+                launch_check_lmax_division((unsigned)ctx->sm_count * 8u, ctx->stream, max_lum, rc, flag);
+                CU_TRY(ctx, cudaGetLastError());
+                CU_TRY(ctx, cudaMemcpyAsync(&bad, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                ctx->launches++;
+                ctx->lmax_div_lmax = max_lum;
+                ctx->lmax_div_rc = bad ? 0.0f : rc;
+                ctx->lmax_div_checked = true;
+            } else {
+                ctx->err.clear();
+            }
+        }
+        if (ctx->lmax_div_checked)
+            q.lmax_rc = ctx->lmax_div_rc;
+    }
     if (!ctx->pq_valid || memcmp(&ctx->pq_lmax, &max_lum, sizeof(float)) != 0) {
         ctx->pq_valid = false;
         if (reserve(ctx, ctx->d_pq, kPqTabPqdBytes + kPqTabPqeBytes) != LUMACU_OK) {
@@ -1311,8 +1340,8 @@ static int encode_launch(lumacu_ctx *ctx, const float *d_rgb, float *d_rgb_out, 
 
     EncArgs a{};
     a.q = ctx->q;
-    if (ctx->pq_off)
-        a.q.pqd = nullptr, a.q.pqe = nullptr, a.q.vdtab = nullptr;
+    if (ctx->pq_off) /* every powf and every division evaluated the long way */
+        a.q.pqd = nullptr, a.q.pqe = nullptr, a.q.vdtab = nullptr, a.q.lmax_rc = 0.0f;
     a.rgb = d_rgb;
     a.rgb_out = d_rgb_out;
     a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
