@@ -383,6 +383,7 @@ int lumacu_set_host_bands(lumacu_ctx *ctx, int bands);
  *            + 1000  bucket + threshold luma search where a direct search table would be used
  *            + 2000  the (32-bit-entry) direct search table read from global memory instead of staged into shared memory
  *   dec_variant   4  plain loads;  24  + L2 prefetch of the next tile's code words (the default);  64, 3, 5, 13-15 headline only
+ *            + 2000  CS_YCBCR: the green of both pixels of a pair is evaluated (two exact powf) instead of every other one
  *   blocks_per_sm_cap   cap on the resident blocks per SM of the persistent grid (0 = what the occupancy calculator allows),
  *                    + 100 * T sizes the blocks of a multi-frame launch for T tiles per thread. */
 int lumacu_set_tuning(lumacu_ctx *ctx, int enc_variant, int dec_variant, int blocks_per_sm_cap);

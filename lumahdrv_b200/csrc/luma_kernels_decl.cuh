@@ -50,6 +50,7 @@ struct QuantDev {
      * FMAs) -- proved equal to the IEEE quotient for EVERY float val >= 1e-10 by an exhaustive device check at
      * set_quantizer time (luma_pq_tables.cuh check_lmax_division_kernel); 0 = divide */
     float lmax_rc;
+    uint32_t tune_flags; /* tuning sweeps: bit 0 = CS_YCBCR decode evaluates the green of both pixels of a pair */
 };
 
 constexpr int kThreads = 256;

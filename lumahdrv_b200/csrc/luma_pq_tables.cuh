@@ -276,11 +276,13 @@ static __device__ __noinline__ Float3x2 ycbcr_inverse_px2_tab(const QuantDev &q,
     /* A lookup costs one 32-byte L2 sector; on content without locality (noise) three of them per pixel saturate the
      * L2 (~235 G sectors/s on B200: 79 kMpx/s) while the SMs idle.  So the green of every other pixel is EVALUATED (two
      * exact powf, ~220 instructions) instead of looked up: both resources busy.  Measured on 4K noise, decode:
-     * 1.19 TB/s-equivalent all looked up, 1.26 with every green evaluated, 1.29 with every other one. */
+     * 1.19 TB/s-equivalent all looked up, 1.26 with every green evaluated, 1.29 with every other one.  Re-measured with
+     * the fused powf (scripts/ycbcr_green_probe.py, decoder tuning 2000 = every green): 771 vs 767 us per 8 frames on
+     * noise, 589 vs 637 us on the reference's test pattern -- every other one stays. */
     float o[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        if (i == 1 && q.pqd) /* green of the first pixel of the pair */
+        if ((i == 1 || (i == 4 && (q.tune_flags & 1u))) && q.pqd) /* green of the first pixel of the pair (tuning: of both) */
             o[i] = (v[i] == 0.0f) ? __fmul_rn(l_max, 0.0f) : pq_decode(v[i], l_max);
         else
             o[i] = pq_decode_tab(q, v[i], l_max);

@@ -1160,7 +1160,7 @@ try {
     ctx->no_direct = enc_variant >= 1000 && enc_variant < 2000; /* 1000 + variant: bucket + threshold search instead of the direct table */
     ctx->global_direct = enc_variant >= 2000;                   /* 2000 + variant: direct table read from global memory (no staging) */
     ctx->enc_variant = enc_variant % 1000;
-    ctx->dec_variant = dec_variant;
+    ctx->dec_variant = dec_variant; /* 2000 + v: CS_YCBCR decode evaluates both greens of a pixel pair (luma_pq_tables.cuh) */
     ctx->grid_cap = blocks_per_sm_cap % 100;     /* blocks_per_sm_cap = cap + 100 * tiles_per_thread */
     ctx->grid_tpt = blocks_per_sm_cap / 100;
     return LUMACU_OK;
@@ -1504,6 +1504,7 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
     a.q = ctx->q;
     if (ctx->pq_off)
         a.q.pqd = nullptr, a.q.pqe = nullptr;
+    a.q.tune_flags = ctx->dec_variant >= 2000 ? 1u : 0u;
     a.rgb = d_rgb;
     a.rgb_plane_stride = opt.rgb_plane_stride ? opt.rgb_plane_stride : (size_t)w * h;
     a.rgb_frame_stride = rgb_frame_stride ? rgb_frame_stride : (size_t)3 * w * h;
@@ -1553,7 +1554,7 @@ static int decode_launch(lumacu_ctx *ctx, const uint8_t *const d_planes[3], cons
         return LUMACU_OK;
     }
     if (vec && small32 && ctx->smem_dec_fast && !ctx->force_generic && !opt.passthrough && !opt.display) {
-        fn = pick_dec_fast(ctx->color_space, sub, bytes, ctx->dec_variant ? ctx->dec_variant : kDecDefaultVariant);
+        fn = pick_dec_fast(ctx->color_space, sub, bytes, (ctx->dec_variant % 2000) ? ctx->dec_variant % 2000 : kDecDefaultVariant);
         if (!fn)
             fn = pick_dec_fast(ctx->color_space, sub, bytes, kDecVariantPlain);
         smem = ctx->smem_dec_fast;

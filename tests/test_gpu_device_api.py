@@ -546,6 +546,10 @@ def test_ycbcr_pq_tables_equal_per_pixel_powf(lumalib, po, torch_cuda, lmax, sc)
     a, b = out.view(torch.int32), ref_out.view(torch.int32)
     same = (a == b) | (torch.isnan(out) & torch.isnan(ref_out))
     assert bool(same.all()), f"decode: {(~same).sum().item()} floats differ"
+    ctx.set_tuning(0, 2000, 0)  # green of BOTH pixels of a pair evaluated instead of looked up (sweep knob): same bits
+    both = t.decode(planes, w, h)
+    ctx.set_tuning(0, 0, 0)
+    assert bool(((both.view(torch.int32) == b) | (torch.isnan(both) & torch.isnan(ref_out))).all())
     # the host libm's word on one frame of each
     o = po.Oracle().setQuantizer("PQ", 10, "YCBCR", 10, lmax, 0.01)
     for f in (0, n - 2, n - 1):
