@@ -89,7 +89,7 @@ static __device__ __noinline__ float powf_glibc_rare(float x, float y);
  * every B200 host -- and scripts/powchk.c compares both contraction choices with the host powf for EVERY positive normal
  * float and the four PQ exponents (4 x 2 130 706 432 inputs, profiles/r02_powf_exhaustive.log): the fused sequence
  * equals libm on all of them; the unfused one (rounds 1 and early 2 of this file, 27 operations instead of 18) differs
- * for one input each of y = 1/0.1593f (x = 0x1.7b1e06p-11, reachable by PQ decode) and y = 78.8438f (x > 1, not
+ * for one input each of y = 1/0.1593f (x = 0x1.7b1e06p-11; no v in (0,1] leads PQ decode there) and y = 78.8438f (x > 1, not
  * reachable).
  * RANGE_CHECK = false: for callers whose exponent cannot overflow or underflow a positive normal x (|y| < 0.85:
  * 0.1593f and 1/78.8438f), the |y log2 x| >= 126 test is dropped. */
