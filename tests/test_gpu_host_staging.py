@@ -275,3 +275,40 @@ def test_half_rgba_rejects_luminance_only_files(lumalib):
     enc.initialize(None, 64, 32)
     with pytest.raises(L.LumaException, match="luminance only"):
         enc.encode_half_rgba(np.zeros((32, 64, 4), np.float16), channels=16)
+
+
+@pytest.mark.parametrize("bits,cs,cbits,lmax", [(10, "YCBCR", 10, 1000.0), (16, "LUV", 8, 1e4), (12, "LUV", 12, 1e4)])
+def test_broadcast_carries_every_table_flavour(lumalib, po, bits, cs, cbits, lmax):
+    """lumacu_broadcast_quantizer with the quantizers whose device state is more than LUT + thresholds: CS_YCBCR (PQ tables,
+    v-keyed search table and the verified Lmax reciprocal are rebuilt on the receiving device), a 16-bit LUT (direct table
+    in global memory, decode LUT read in place) and a 12-bit one (64-bit two-threshold table).  The receiver -- on the
+    next device when there is one -- must produce the oracle's planes and floats and run the tuned kernels."""
+    import ctypes as C
+
+    import torch
+    L = lumalib
+    lib = L.lib()
+    n_dev = torch.cuda.device_count()
+    root, recv = L.Context(0), L.Context(1 % n_dev)
+    lut = L.build_lut("PQ", bits, lmax, 0.005)
+    cs_id = {"LUV": L.CS_LUV, "YCBCR": L.CS_YCBCR}[cs]
+    L._lib.check(lib.lumacu_set_quantizer(root.handle, lut.ctypes.data, lut.size, (1 << cbits) - 1, cs_id, lmax), root.handle, "set")
+    arr = (C.c_void_p * 2)(root.handle, recv.handle)
+    assert lib.lumacu_broadcast_quantizer(arr, 2, 0) == 0
+    o = po.Oracle().setQuantizer("PQ", bits, cs, cbits, lmax, 0.005)
+    w, h = 1024, 256
+    frame = po.noise_frame(w, h, seed=bits)
+    ref_planes, _ = o.encode(frame.copy(), 2, 1.0)
+    ref_out = o.decode(ref_planes, w, h, 2, 1.0)
+    planes = L.alloc_planes(w, h, 2)
+    ptrs, st = L.luma._plane_args(planes)
+    stats = L._lib.FrameStats()
+    f = frame.copy()
+    L._lib.check(lib.lumacu_encode(recv.handle, f.ctypes.data, w, h, 2, 1.0, ptrs, st, 0, C.byref(stats)), recv.handle, "encode")
+    assert lib.lumacu_last_kernel_path(recv.handle) == 1
+    for a, b, (pw, ph) in zip(planes, ref_planes, po.plane_dims(w, h, 2)):
+        assert np.array_equal(a[:ph, :pw * 2], b[:ph, :pw * 2])
+    out = np.empty((3, h, w), np.float32)
+    L._lib.check(lib.lumacu_decode(recv.handle, ptrs, st, w, h, 2, 1.0, out.ctypes.data), recv.handle, "decode")
+    assert lib.lumacu_last_kernel_path(recv.handle) == 1
+    assert bits_equal(out, ref_out)
