@@ -1,5 +1,13 @@
-import sys, time
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python
+"""How long do lumacu_set_quantizer and a new context take?  CS_YCBCR builds 45 MB of PQ tables, the v-keyed search table and
+runs the exhaustive val / Lmax division check (1.35e9 operands) per new Lmax; Lu'v' only derives thresholds on the host.
+Measured on B200: 1.6 ms for a CS_YCBCR quantizer with a new Lmax, 0.4 ms with a known one, 0.23 ms for Lu'v', 8-14 ms for a
+new context + quantizer."""
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from lumahdrv_b200.device import DeviceTransform
 t = DeviceTransform(0, ptf="PQ", ptfBitDepth=10, colorSpace="YCBCR", colorBitDepth=10)
